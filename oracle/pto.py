@@ -1,0 +1,174 @@
+"""ctypes binding of the CPU oracle (oracle/libpt_oracle.so).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/pt_oracle.h.  Imported by tests/,
+``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference``
+legs; never by the product package.  PARITY UNPINNED (no reference goldens).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpt_oracle.so")
+
+# Byte-for-byte mirror of the reference ``struct Point`` (src/Point.h:1-6).
+POINT_DTYPE = np.dtype(
+    [("ver", "<f8", 3), ("normal", "<f8", 3), ("color", "<i4", 3), ("pad_", "<i4"),
+     ("U", "<f8"), ("V", "<f8")]
+)
+assert POINT_DTYPE.itemsize == 80
+
+
+def build(force=False):
+    """Compile the C restatement (gcc, oracle/Makefile)."""
+    if force or not os.path.exists(_LIB_PATH) or (
+        os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f))
+                                          for f in ("pt_oracle.c", "pt_oracle.h"))
+    ):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, i64, i32, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
+        L.pto_transformed_distance.restype = dbl
+        L.pto_transformed_distance.argtypes = [vp, vp]
+        L.pto_min_distance_to_rectangle.restype = dbl
+        L.pto_min_distance_to_rectangle.argtypes = [vp, vp, vp, vp]
+        L.pto_new_distance.restype = dbl
+        L.pto_new_distance.argtypes = [dbl, dbl, dbl]
+        L.pto_transformed_radius.restype = dbl
+        L.pto_transformed_radius.argtypes = [dbl]
+        L.pto_knn_bruteforce.restype = i32
+        L.pto_knn_bruteforce.argtypes = [vp, i64, vp, i64, i32, dbl, vp, vp, i32]
+        L.pto_blend.restype = i32
+        L.pto_blend.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp]
+        L.pto_kdtree_build.restype = vp
+        L.pto_kdtree_build.argtypes = [vp, i64, i32]
+        L.pto_kdtree_free.restype = None
+        L.pto_kdtree_free.argtypes = [vp]
+        L.pto_kdtree_node_count.restype = i64
+        L.pto_kdtree_node_count.argtypes = [vp]
+        L.pto_kdtree_knn.restype = i32
+        L.pto_kdtree_knn.argtypes = [vp, vp, i64, i32, dbl, i32, vp, vp, i32]
+        L.pto_reference_face_loop.restype = i64
+        L.pto_reference_face_loop.argtypes = [vp, vp, vp, i64, i32, i32]
+        L.pto_max_threads.restype = i32
+        _lib = L
+    return _lib
+
+
+def make_points(xyz, normal=None, color=None, uv=None):
+    """Pack arrays into the 80-byte AoS ``Point`` records."""
+    xyz = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
+    p = np.zeros(xyz.shape[0], dtype=POINT_DTYPE)
+    p["ver"] = xyz
+    if normal is not None:
+        p["normal"] = np.asarray(normal, dtype=np.float64).reshape(-1, 3)
+    if color is not None:
+        p["color"] = np.asarray(color, dtype=np.int32).reshape(-1, 3)
+    if uv is not None:
+        uv = np.asarray(uv, dtype=np.float64).reshape(-1, 2)
+        p["U"], p["V"] = uv[:, 0], uv[:, 1]
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _chk_points(a):
+    a = np.ascontiguousarray(a)
+    assert a.dtype == POINT_DTYPE, a.dtype
+    return a
+
+
+def transformed_distance(p1, p2):
+    a, b = _chk_points(p1.reshape(1)), _chk_points(p2.reshape(1))
+    return lib().pto_transformed_distance(_ptr(a), _ptr(b))
+
+
+def min_distance_to_rectangle(p, lo, hi, dists=None):
+    a = _chk_points(p.reshape(1))
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    d = np.zeros(3) if dists is None else dists
+    return lib().pto_min_distance_to_rectangle(_ptr(a), _ptr(lo), _ptr(hi), _ptr(d)), d
+
+
+def knn_bruteforce(points, queries, k, radius=-1.0, nthreads=0, want_d2=True):
+    points, queries = _chk_points(points), _chk_points(queries)
+    m = queries.shape[0]
+    idx = np.empty((m, k), dtype=np.int32)
+    d2 = np.empty((m, k), dtype=np.float64) if want_d2 else None
+    rc = lib().pto_knn_bruteforce(_ptr(points), points.shape[0], _ptr(queries), m, k,
+                                  float(radius), _ptr(idx), _ptr(d2) if want_d2 else None,
+                                  nthreads)
+    assert rc == 0, rc
+    return idx, d2
+
+
+def blend(points, idx, d2):
+    points = _chk_points(points)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    d2 = np.ascontiguousarray(d2, dtype=np.float64)
+    m, k = idx.shape
+    rgba = np.empty((m, 4), dtype=np.uint8)
+    nrm = np.empty((m, 3), dtype=np.float32)
+    rc = lib().pto_blend(_ptr(points), points.shape[0], m, k, _ptr(idx), _ptr(d2),
+                         _ptr(rgba), _ptr(nrm))
+    assert rc == 0, rc
+    return rgba, nrm
+
+
+class KdTree:
+    """The reference's CPU path restated: ``Tree tree(points.begin(), points.end())``
+    (src/pointsTransfer.cpp:259) + ``K_neighbor_search`` (:474)."""
+
+    def __init__(self, points, bucket_size=10):
+        self._points = _chk_points(points)
+        self._h = lib().pto_kdtree_build(_ptr(self._points), self._points.shape[0], bucket_size)
+        assert self._h
+
+    def close(self):
+        if self._h:
+            lib().pto_kdtree_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def node_count(self):
+        return lib().pto_kdtree_node_count(self._h)
+
+    def knn(self, queries, k, radius=-1.0, exact_ties=True, nthreads=0, want_d2=True):
+        queries = _chk_points(queries)
+        m = queries.shape[0]
+        idx = np.empty((m, k), dtype=np.int32)
+        d2 = np.empty((m, k), dtype=np.float64) if want_d2 else None
+        rc = lib().pto_kdtree_knn(self._h, _ptr(queries), m, k, float(radius),
+                                  1 if exact_ties else 0, _ptr(idx),
+                                  _ptr(d2) if want_d2 else None, nthreads)
+        assert rc == 0, rc
+        return idx, d2
+
+    def reference_face_loop(self, vertices, faces, k, nthreads=0):
+        vertices = _chk_points(vertices)
+        faces = np.ascontiguousarray(faces, dtype=np.int32)
+        return lib().pto_reference_face_loop(self._h, _ptr(vertices), _ptr(faces),
+                                             faces.shape[0], k, nthreads)
+
+
+def max_threads():
+    return lib().pto_max_threads()
