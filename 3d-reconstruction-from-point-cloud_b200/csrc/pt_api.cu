@@ -1,0 +1,324 @@
+// pt_api.cu -- the C ABI (include/points_transfer.h).  Thin: argument checks, device memory
+// and stream plumbing, then the kernels in pt_build.cu / pt_knn.cu.  No CPU fallback exists:
+// without a CUDA device every compute entry point returns PT_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "pt_index.cuh"
+
+namespace pt {
+
+std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_verbose{-1};
+static std::atomic<int> g_knn_variant{0};
+static std::atomic<int> g_order{0};
+
+bool verbose()
+{
+    int v = g_verbose.load();
+    if (v < 0) {
+        const char *e = getenv("PT_VERBOSE");
+        v = (e && *e && *e != '0') ? 1 : 0;
+        g_verbose.store(v);
+    }
+    return v != 0;
+}
+
+int map_cuda_error(cudaError_t e)
+{
+    switch (e) {
+        case cudaSuccess: return PT_OK;
+        case cudaErrorMemoryAllocation: return PT_ERR_OUT_OF_MEMORY;
+        case cudaErrorNoDevice:
+        case cudaErrorInsufficientDriver:
+        case cudaErrorInvalidDevice: return PT_ERR_NO_DEVICE;
+        default: return PT_ERR_CUDA;
+    }
+}
+
+int opt_knn_variant() { return g_knn_variant.load(); }
+int opt_order() { return g_order.load(); }
+
+int set_option(const char *name, int value)
+{
+    if (!name) return PT_ERR_INVALID_ARG;
+    if (!strcmp(name, "knn_variant")) { g_knn_variant.store(value); return PT_OK; }
+    if (!strcmp(name, "order")) { g_order.store(value); return PT_OK; }
+    if (!strcmp(name, "verbose")) { g_verbose.store(value ? 1 : 0); return PT_OK; }
+    return PT_ERR_INVALID_ARG;
+}
+int get_option(const char *name, int *value)
+{
+    if (!name || !value) return PT_ERR_INVALID_ARG;
+    if (!strcmp(name, "knn_variant")) { *value = g_knn_variant.load(); return PT_OK; }
+    if (!strcmp(name, "order")) { *value = g_order.load(); return PT_OK; }
+    if (!strcmp(name, "verbose")) { *value = verbose() ? 1 : 0; return PT_OK; }
+    return PT_ERR_INVALID_ARG;
+}
+
+static int grow(void **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return PT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4;
+    PT_CUDA(cudaMalloc(p, want));
+    *cap = want;
+    return PT_OK;
+}
+
+static int new_index(int device, pt_index **out)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) { cudaGetLastError(); return PT_ERR_NO_DEVICE; }
+    if (device < 0) PT_CUDA(cudaGetDevice(&device));
+    if (device >= count) return PT_ERR_INVALID_ARG;
+    PT_CUDA(cudaSetDevice(device));
+    pt_index *ix = new (std::nothrow) pt_index();
+    if (!ix) return PT_ERR_OUT_OF_MEMORY;
+    ix->device = device;
+    PT_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto &ev : ix->ev) PT_CUDA(cudaEventCreate(&ev));
+    *out = ix;
+    return PT_OK;
+}
+
+static void destroy_index(pt_index *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    cudaFree(ix->pts); cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->boxes);
+    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out);
+    for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+static double radius_to_r2(double radius)
+{
+    if (!(radius >= 0.0) || std::isinf(radius)) return INFINITY;
+    return radius * radius;  // Distance::transformed_distance(d), src/Distance.h:97
+}
+
+static void fill_params(const pt_index *ix, QueryParams &qp)
+{
+    qp.pts = ix->pts;
+    qp.attrs = ix->attrs;
+    qp.ids = ix->ids;
+    qp.pyr = ix->pyr;
+    qp.n = ix->n;
+    qp.n_leaves = ix->n_leaves;
+    qp.w_levels = ix->w_levels;
+}
+
+}  // namespace pt
+
+using namespace pt;
+
+extern "C" {
+
+const char *pt_version(void) { return "points_transfer_b200 0.1 (sm_100a)"; }
+
+const char *pt_status_string(int status)
+{
+    switch (status) {
+        case PT_OK: return "ok";
+        case PT_ERR_INVALID_ARG: return "invalid argument";
+        case PT_ERR_CUDA: return "CUDA error";
+        case PT_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case PT_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case PT_ERR_UNSUPPORTED: return "unsupported parameter (k must be 1..32)";
+        case PT_ERR_NOT_REPRESENTABLE: return "cloud coordinates are not fp32-representable";
+        case PT_ERR_NON_FINITE: return "non-finite coordinate in the cloud";
+        default: return "unknown status";
+    }
+}
+
+int pt_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+uint64_t pt_kernel_launch_count(void) { return g_launches.load(); }
+int pt_set_option(const char *name, int value) { return set_option(name, value); }
+int pt_get_option(const char *name, int *value) { return get_option(name, value); }
+
+int pt_index_build(const void *points, size_t n, const pt_build_opts *opts, pt_index **out)
+{
+    if (!out || (!points && n) || n >= 0x7fffffffull) return PT_ERR_INVALID_ARG;
+    *out = nullptr;
+    int device = opts ? opts->device : -1;
+    int mode = opts ? opts->coord_mode : PT_COORD_AUTO;
+    if (mode < PT_COORD_AUTO || mode > PT_COORD_F64) return PT_ERR_INVALID_ARG;
+    pt_index *ix = nullptr;
+    PT_TRY(new_index(device, &ix));
+    double *xyz = nullptr;
+    bool representable = true;
+    int rc = ingest_points_aos(ix, points, n, mode, &xyz, &representable);
+    if (rc == PT_OK && mode == PT_COORD_F32 && !representable) rc = PT_ERR_NOT_REPRESENTABLE;
+    if (rc == PT_OK && opts && opts->ids && n) {
+        cudaError_t e = cudaMalloc(&ix->ids, sizeof(int32_t) * n);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ix->ids, opts->ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice,
+                                ix->stream);
+        rc = map_cuda_error(e);
+    }
+    if (rc == PT_OK) {
+        bool f64 = mode == PT_COORD_F64 || (mode == PT_COORD_AUTO && !representable);
+        rc = build_index_d3(ix, xyz, (uint32_t)n, f64);
+    }
+    cudaFree(xyz);
+    if (rc != PT_OK) { destroy_index(ix); return rc; }
+    *out = ix;
+    return PT_OK;
+}
+
+int pt_index_build_device(const void *pos, int coord_f64, const pt_attr *attrs,
+                          const int32_t *ids, size_t n, int device, pt_index **out)
+{
+    if (!out || (!pos && n) || n >= 0x7fffffffull) return PT_ERR_INVALID_ARG;
+    *out = nullptr;
+    pt_index *ix = nullptr;
+    PT_TRY(new_index(device, &ix));
+    int rc = PT_OK;
+    if (n && attrs) {
+        cudaError_t e = cudaMalloc(&ix->attrs, sizeof(pt_attr) * n);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ix->attrs, attrs, sizeof(pt_attr) * n, cudaMemcpyDeviceToDevice,
+                                ix->stream);
+        rc = map_cuda_error(e);
+    }
+    if (rc == PT_OK && n && ids) {
+        cudaError_t e = cudaMalloc(&ix->ids, sizeof(int32_t) * n);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ix->ids, ids, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice,
+                                ix->stream);
+        rc = map_cuda_error(e);
+    }
+    if (rc == PT_OK)
+        rc = coord_f64 ? build_index_d4(ix, (const double *)pos, (uint32_t)n, true)
+                       : build_index_f4(ix, (const float4 *)pos, (uint32_t)n, false);
+    if (rc != PT_OK) { destroy_index(ix); return rc; }
+    *out = ix;
+    return PT_OK;
+}
+
+int pt_index_free(pt_index *index)
+{
+    destroy_index(index);
+    return PT_OK;
+}
+
+int pt_index_get_info(const pt_index *ix, pt_index_info *info)
+{
+    if (!ix || !info) return PT_ERR_INVALID_ARG;
+    memset(info, 0, sizeof *info);
+    info->n_points = ix->n;
+    info->n_leaves = ix->n_leaves;
+    info->n_levels = ix->pyr.n_levels;
+    info->coord_mode = ix->coord_f64 ? PT_COORD_F64 : PT_COORD_F32;
+    info->device = ix->device;
+    for (int a = 0; a < 3; ++a) { info->bbox_lo[a] = ix->bb_lo[a]; info->bbox_hi[a] = ix->bb_hi[a]; }
+    info->device_bytes = ix->device_bytes;
+    info->build_ms = ix->build_ms;
+    info->last_query_ms = ix->last_query_ms;
+    info->last_h2d_ms = ix->last_h2d_ms;
+    info->last_d2h_ms = ix->last_d2h_ms;
+    return PT_OK;
+}
+
+int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, double radius,
+                    const double *radius2_per_query, int32_t *idx_out, double *d2_out,
+                    uint8_t *rgba_out, float *normal_out, pt_cand *cand_out, void *stream)
+{
+    if (!ix || (!queries_xyz && m) || m > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
+    if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
+    if ((rgba_out || normal_out) && !ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
+    PT_CUDA(cudaSetDevice(ix->device));
+    QueryParams qp{};
+    fill_params(ix, qp);
+    qp.queries = queries_xyz;
+    qp.r2_per_query = radius2_per_query;
+    qp.m = (uint32_t)m;
+    qp.k = k;
+    qp.r2 = radius_to_r2(radius);
+    qp.idx_out = idx_out; qp.d2_out = d2_out; qp.rgba_out = rgba_out;
+    qp.normal_out = normal_out; qp.cand_out = cand_out;
+    return launch_query(ix, qp, stream ? (cudaStream_t)stream : ix->stream);
+}
+
+int pt_merge_device(const pt_cand *lists, int n_lists, size_t m, int k, int32_t *idx_out,
+                    double *d2_out, uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
+                    int device, void *stream)
+{
+    if ((!lists && m) || m > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
+    if (pt_device_count() == 0) return PT_ERR_NO_DEVICE;
+    if (device >= 0) PT_CUDA(cudaSetDevice(device));
+    return launch_merge(lists, n_lists, (uint32_t)m, k, idx_out, d2_out, rgba_out, normal_out,
+                        cand_out, (cudaStream_t)stream);
+}
+
+static int host_query(pt_index *ix, const void *queries, size_t m, int k, double radius,
+                      int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out)
+{
+    if (!ix || (!queries && m) || m > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
+    if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
+    if (m == 0) return PT_OK;
+    PT_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t s = ix->stream;
+    const size_t mk = m * (size_t)k;
+    // output workspace layout: d2 | idx | normal | rgba (descending alignment)
+    size_t off_d2 = 0, off_idx = off_d2 + (d2_out ? mk * 8 : 0);
+    size_t off_nrm = off_idx + (idx_out ? mk * 4 : 0);
+    size_t off_rgba = off_nrm + (normal_out ? m * 12 : 0);
+    size_t total = off_rgba + (rgba_out ? m * 4 : 0);
+    PT_TRY(grow(&ix->ws_raw, &ix->ws_raw_bytes, m * PT_POINT_STRIDE));
+    PT_TRY(grow(&ix->ws_q, &ix->ws_q_bytes, m * 24));
+    PT_TRY(grow(&ix->ws_out, &ix->ws_out_bytes, total ? total : 16));
+    char *o = (char *)ix->ws_out;
+
+    PT_CUDA(cudaEventRecord(ix->ev[0], s));
+    PT_CUDA(cudaMemcpyAsync(ix->ws_raw, queries, m * PT_POINT_STRIDE, cudaMemcpyHostToDevice, s));
+    PT_TRY(unpack_queries_aos(ix->ws_raw, m, (double *)ix->ws_q, s));
+    PT_CUDA(cudaEventRecord(ix->ev[1], s));
+    int rc = pt_query_device(ix, (const double *)ix->ws_q, m, k, radius, nullptr,
+                             idx_out ? (int32_t *)(o + off_idx) : nullptr,
+                             d2_out ? (double *)(o + off_d2) : nullptr,
+                             rgba_out ? (uint8_t *)(o + off_rgba) : nullptr,
+                             normal_out ? (float *)(o + off_nrm) : nullptr, nullptr, s);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaEventRecord(ix->ev[2], s));
+    if (d2_out) PT_CUDA(cudaMemcpyAsync(d2_out, o + off_d2, mk * 8, cudaMemcpyDeviceToHost, s));
+    if (idx_out) PT_CUDA(cudaMemcpyAsync(idx_out, o + off_idx, mk * 4, cudaMemcpyDeviceToHost, s));
+    if (normal_out) PT_CUDA(cudaMemcpyAsync(normal_out, o + off_nrm, m * 12, cudaMemcpyDeviceToHost, s));
+    if (rgba_out) PT_CUDA(cudaMemcpyAsync(rgba_out, o + off_rgba, m * 4, cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaEventRecord(ix->ev[3], s));
+    PT_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ix->last_h2d_ms, ix->ev[0], ix->ev[1]);
+    cudaEventElapsedTime(&ix->last_query_ms, ix->ev[1], ix->ev[2]);
+    cudaEventElapsedTime(&ix->last_d2h_ms, ix->ev[2], ix->ev[3]);
+    return PT_OK;
+}
+
+int pt_knn(pt_index *index, const void *queries, size_t m, int k, double radius,
+           int32_t *idx_out, double *d2_out)
+{
+    if (!idx_out && m) return PT_ERR_INVALID_ARG;
+    return host_query(index, queries, m, k, radius, idx_out, d2_out, nullptr, nullptr);
+}
+
+int pt_transfer(pt_index *index, const void *queries, size_t m, int k, double radius,
+                int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out)
+{
+    if ((!rgba_out && !normal_out) && m) return PT_ERR_INVALID_ARG;
+    return host_query(index, queries, m, k, radius, idx_out, d2_out, rgba_out, normal_out);
+}
+
+}  // extern "C"

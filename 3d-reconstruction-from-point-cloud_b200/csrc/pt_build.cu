@@ -1,0 +1,423 @@
+// pt_build.cu -- spatial index build (replaces the lazy CGAL kd-tree build behind
+// `Tree tree(points.begin(), points.end())`, /root/reference src/pointsTransfer.cpp:259).
+//
+//   K1  bounding box + 63-bit Morton key per point        (bbox_kernel, morton_kernel)
+//   K2  radix sort of (key, index) pairs                   (sort_pairs)
+//       gather into 32-point leaves (16-byte float4 / 32-byte fp64 records)
+//       leaf boxes + binary box pyramid ("cell table")    (leaf_box_kernel, pyramid_kernel)
+//
+// HBM layout: pts[n_leaves*32] sorted records; boxes[level][node] 32-byte AABBs, level j
+// node i covering leaves [i*2^j, (i+1)*2^j).  Attributes and ids stay in original order.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cfloat>
+#include <cmath>
+
+#include "pt_index.cuh"
+
+namespace pt {
+
+// ---- K1: bounding box -------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long enc_f64(double d)
+{
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+static inline double dec_f64(unsigned long long u)
+{
+    u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    double d;
+    memcpy(&d, &u, sizeof d);
+    return d;
+}
+
+struct BBoxAcc {                 // device-side accumulator
+    unsigned long long lo[3];    // encoded minima
+    unsigned long long hi[3];    // encoded maxima
+    unsigned int       non_finite;
+    unsigned int       pad;
+};
+
+template <typename In>
+__global__ void __launch_bounds__(256) bbox_kernel(In in, uint32_t n, BBoxAcc *acc)
+{
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool bad = false;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double v[3];
+        in.load(i, v[0], v[1], v[2]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            bad |= !isfinite(v[a]);
+            lo[a] = fmin(lo[a], v[a]);
+            hi[a] = fmax(hi[a], v[a]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], s));
+            hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], s));
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&acc->lo[a], enc_f64(lo[a]));
+            atomicMax(&acc->hi[a], enc_f64(hi[a]));
+        }
+        if (bad) atomicOr(&acc->non_finite, 1u);
+    }
+}
+
+// ---- K1: Morton keys ----------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long spread21(unsigned int v)
+{
+    unsigned long long x = v & 0x1fffffu;
+    x = (x | (x << 32)) & 0x001f00000000ffffull;
+    x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+    x = (x | (x << 8)) & 0x100f00f00f00f00full;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+struct KeyParams {
+    double lo[3];
+    double inv_cell;   // 2^21 / max extent (0 when the cloud is a single point)
+};
+
+template <typename In>
+__global__ void __launch_bounds__(256) morton_kernel(In in, uint32_t n, KeyParams kp,
+                                                     unsigned long long *keys, uint32_t *vals)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v[3];
+    in.load(i, v[0], v[1], v[2]);
+    unsigned int c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double t = (v[a] - kp.lo[a]) * kp.inv_cell;
+        t = fmin(fmax(t, 0.0), 2097151.0);
+        c[a] = (unsigned int)t;
+    }
+    keys[i] = spread21(c[0]) | (spread21(c[1]) << 1) | (spread21(c[2]) << 2);
+    vals[i] = i;
+}
+
+// ---- gather into leaves -----------------------------------------------------------------
+template <typename In, typename Out>
+__global__ void __launch_bounds__(256) gather_kernel(In in, const uint32_t *perm, uint32_t n,
+                                                     uint32_t n_pad, Out *out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    Out o;
+    if (i < n) {
+        uint32_t src = perm[i];
+        double x, y, z;
+        in.load(src, x, y, z);
+        o.x = x; o.y = y; o.z = z;   // exact: F32 storage is only chosen when representable
+        o.idx = (int)src;
+    } else {
+        o.x = FLT_MAX; o.y = FLT_MAX; o.z = FLT_MAX;
+        o.idx = IDX_NONE;
+    }
+    if constexpr (sizeof(Out) == 32) o.pad = 0;
+    out[i] = o;
+}
+
+// ---- leaf boxes: one warp per 32-point leaf ------------------------------------------------
+__device__ __forceinline__ float f_dn(double v) { return __double2float_rd(v); }
+__device__ __forceinline__ float f_up(double v) { return __double2float_ru(v); }
+
+template <typename Out>
+__global__ void __launch_bounds__(256) leaf_box_kernel(const Out *pts, uint32_t n,
+                                                       uint32_t n_leaves, Box *boxes)
+{
+    uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (leaf >= n_leaves) return;
+    uint32_t i = leaf * LEAF + lane;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (i < n) {
+        Out p = pts[i];
+        lo[0] = f_dn(p.x); lo[1] = f_dn(p.y); lo[2] = f_dn(p.z);
+        hi[0] = f_up(p.x); hi[1] = f_up(p.y); hi[2] = f_up(p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], s));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], s));
+        }
+    }
+    if (lane == 0) {
+        Box b;
+        b.lox = lo[0]; b.loy = lo[1]; b.loz = lo[2];
+        b.hix = hi[0]; b.hiy = hi[1]; b.hiz = hi[2];
+        b.pad0 = 0.f; b.pad1 = 0.f;
+        boxes[leaf] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) pyramid_kernel(const Box *child, uint32_t n_child,
+                                                      Box *parent, uint32_t n_parent)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_parent) return;
+    Box a = child[2 * i];
+    if (2 * i + 1 < n_child) {
+        Box b = child[2 * i + 1];
+        a.lox = fminf(a.lox, b.lox); a.loy = fminf(a.loy, b.loy); a.loz = fminf(a.loz, b.loz);
+        a.hix = fmaxf(a.hix, b.hix); a.hiy = fmaxf(a.hiy, b.hiy); a.hiz = fmaxf(a.hiz, b.hiz);
+    }
+    parent[i] = a;
+}
+
+// ---- K2: sort (library radix sort for now; see DESIGN.md "build") ----------------------------
+static int sort_pairs(unsigned long long *&keys, unsigned long long *keys_alt, uint32_t *&vals,
+                      uint32_t *vals_alt, uint32_t n, cudaStream_t s)
+{
+    cub::DoubleBuffer<unsigned long long> dk(keys, keys_alt);
+    cub::DoubleBuffer<uint32_t> dv(vals, vals_alt);
+    size_t tmp_bytes = 0;
+    PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, 63, s));
+    void *tmp = nullptr;
+    PT_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)n, 0, 63, s);
+    count_launch(9);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return map_cuda_error(e);
+    if (e2 != cudaSuccess) return map_cuda_error(e2);
+    keys = dk.Current();
+    vals = dv.Current();
+    return PT_OK;
+}
+
+static inline unsigned int cdiv(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
+
+template <typename In, typename Out>
+static int build_impl(pt_index *ix, In in, uint32_t n)
+{
+    cudaStream_t s = ix->stream;
+    PT_CUDA(cudaEventRecord(ix->ev[0], s));
+    ix->n = n;
+    ix->n_leaves = cdiv(n, LEAF);
+    ix->coord_f64 = sizeof(Out) == 32;
+    for (int a = 0; a < 3; ++a) { ix->bb_lo[a] = 0; ix->bb_hi[a] = 0; }
+    ix->pyr = Pyramid{};
+    ix->w_levels = 0;
+    if (n == 0) { ix->build_ms = 0; return PT_OK; }
+
+    // K1: bbox
+    BBoxAcc *acc = nullptr, h_acc;
+    PT_CUDA(cudaMalloc(&acc, sizeof(BBoxAcc)));
+    for (int a = 0; a < 3; ++a) { h_acc.lo[a] = ~0ull; h_acc.hi[a] = 0ull; }
+    h_acc.non_finite = 0; h_acc.pad = 0;
+    PT_CUDA(cudaMemcpyAsync(acc, &h_acc, sizeof h_acc, cudaMemcpyHostToDevice, s));
+    {
+        unsigned int blocks = cdiv(n, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        bbox_kernel<In><<<blocks, 256, 0, s>>>(in, n, acc);
+        count_launch();
+    }
+    PT_CUDA(cudaMemcpyAsync(&h_acc, acc, sizeof h_acc, cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaStreamSynchronize(s));
+    cudaFree(acc);
+    if (h_acc.non_finite) return PT_ERR_NON_FINITE;
+    KeyParams kp;
+    double ext = 0;
+    for (int a = 0; a < 3; ++a) {
+        ix->bb_lo[a] = dec_f64(h_acc.lo[a]);
+        ix->bb_hi[a] = dec_f64(h_acc.hi[a]);
+        kp.lo[a] = ix->bb_lo[a];
+        ext = fmax(ext, ix->bb_hi[a] - ix->bb_lo[a]);
+    }
+    kp.inv_cell = ext > 0 ? 2097152.0 / ext : 0.0;
+    if (!std::isfinite(kp.inv_cell)) kp.inv_cell = 0.0;
+
+    // K1: keys, K2: sort
+    unsigned long long *keys = nullptr, *keys_alt = nullptr;
+    uint32_t *vals = nullptr, *vals_alt = nullptr;
+    PT_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)n));
+    PT_CUDA(cudaMalloc(&keys_alt, sizeof(unsigned long long) * (size_t)n));
+    PT_CUDA(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)n));
+    PT_CUDA(cudaMalloc(&vals_alt, sizeof(uint32_t) * (size_t)n));
+    unsigned long long *keys0 = keys;
+    uint32_t *vals0 = vals;
+    morton_kernel<In><<<cdiv(n, 256), 256, 0, s>>>(in, n, kp, keys, vals);
+    count_launch();
+    int rc = sort_pairs(keys, keys_alt, vals, vals_alt, n, s);
+    if (rc != PT_OK) {
+        cudaFree(keys0); cudaFree(keys_alt); cudaFree(vals0); cudaFree(vals_alt);
+        return rc;
+    }
+
+    // gather into leaves
+    size_t n_pad = (size_t)ix->n_leaves * LEAF;
+    Out *pts = nullptr;
+    PT_CUDA(cudaMalloc(&pts, sizeof(Out) * n_pad));
+    gather_kernel<In, Out><<<cdiv(n_pad, 256), 256, 0, s>>>(in, vals, n, (uint32_t)n_pad, pts);
+    count_launch();
+    ix->pts = pts;
+
+    // box pyramid
+    uint64_t total = 0;
+    uint32_t cnt = ix->n_leaves;
+    int levels = 0;
+    uint32_t counts[MAX_PYR_LEVELS];
+    for (;;) {
+        counts[levels++] = cnt;
+        total += cnt;
+        if (cnt == 1) break;
+        cnt = (cnt + 1) / 2;
+    }
+    PT_CUDA(cudaMalloc(&ix->boxes, sizeof(Box) * total));
+    Box *lvl = ix->boxes;
+    for (int j = 0; j < levels; ++j) {
+        ix->pyr.level[j] = lvl;
+        ix->pyr.count[j] = counts[j];
+        lvl += counts[j];
+    }
+    ix->pyr.n_levels = levels;
+    leaf_box_kernel<Out><<<cdiv((uint64_t)ix->n_leaves * 32, 256), 256, 0, s>>>(
+        pts, n, ix->n_leaves, const_cast<Box *>(ix->pyr.level[0]));
+    count_launch();
+    for (int j = 1; j < levels; ++j) {
+        pyramid_kernel<<<cdiv(counts[j], 256), 256, 0, s>>>(
+            ix->pyr.level[j - 1], counts[j - 1], const_cast<Box *>(ix->pyr.level[j]), counts[j]);
+        count_launch();
+    }
+    int t = 1;
+    for (uint64_t cap = 32; cap < ix->n_leaves; cap *= 32) ++t;
+    ix->w_levels = t;
+
+    PT_CUDA(cudaEventRecord(ix->ev[1], s));
+    PT_CUDA(cudaStreamSynchronize(s));
+    PT_CUDA(cudaEventElapsedTime(&ix->build_ms, ix->ev[0], ix->ev[1]));
+    cudaFree(keys0); cudaFree(keys_alt); cudaFree(vals0); cudaFree(vals_alt);
+    ix->device_bytes = sizeof(Out) * n_pad + sizeof(Box) * total +
+                       (ix->attrs ? sizeof(pt_attr) * (size_t)n : 0) +
+                       (ix->ids ? sizeof(int32_t) * (size_t)n : 0);
+    return PT_OK;
+}
+
+int build_index_f4(pt_index *ix, const float4 *pos, uint32_t n, bool out_f64)
+{
+    InF4 in{pos};
+    return out_f64 ? build_impl<InF4, PointD>(ix, in, n) : build_impl<InF4, PointF>(ix, in, n);
+}
+int build_index_d4(pt_index *ix, const double *pos, uint32_t n, bool out_f64)
+{
+    InD4 in{pos};
+    return out_f64 ? build_impl<InD4, PointD>(ix, in, n) : build_impl<InD4, PointF>(ix, in, n);
+}
+int build_index_d3(pt_index *ix, const double *pos, uint32_t n, bool out_f64)
+{
+    InD3 in{pos};
+    return out_f64 ? build_impl<InD3, PointD>(ix, in, n) : build_impl<InD3, PointF>(ix, in, n);
+}
+
+// ---- ingest of the reference's 80-byte AoS `struct Point` (src/Point.h:1-6) ------------------
+struct Raw80 {
+    double ver[3];
+    double normal[3];
+    int    color[3];
+    int    pad;
+    double U, V;
+};
+static_assert(sizeof(Raw80) == PT_POINT_STRIDE, "Point must be 80 bytes");
+
+__global__ void __launch_bounds__(256) unpack_points_kernel(const Raw80 *raw, uint32_t count,
+                                                            double *xyz, pt_attr *attrs,
+                                                            unsigned int *not_representable)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < count) {
+        const Raw80 &r = raw[i];
+        double x = r.ver[0], y = r.ver[1], z = r.ver[2];
+        xyz[3 * (size_t)i] = x; xyz[3 * (size_t)i + 1] = y; xyz[3 * (size_t)i + 2] = z;
+        bad = ((double)(float)x != x) || ((double)(float)y != y) || ((double)(float)z != z);
+        pt_attr a;
+        a.nx = (float)r.normal[0]; a.ny = (float)r.normal[1]; a.nz = (float)r.normal[2];
+        a.r = (uint8_t)min(max(r.color[0], 0), 255);
+        a.g = (uint8_t)min(max(r.color[1], 0), 255);
+        a.b = (uint8_t)min(max(r.color[2], 0), 255);
+        a.a = 255;
+        attrs[i] = a;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(not_representable, 1u);
+}
+
+__global__ void __launch_bounds__(256) unpack_queries_kernel(const Raw80 *raw, uint32_t m,
+                                                             double *xyz)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    xyz[3 * (size_t)i] = raw[i].ver[0];
+    xyz[3 * (size_t)i + 1] = raw[i].ver[1];
+    xyz[3 * (size_t)i + 2] = raw[i].ver[2];
+}
+
+int unpack_queries_aos(const void *raw80_dev, size_t m, double *xyz_dev, cudaStream_t s)
+{
+    if (m == 0) return PT_OK;
+    unpack_queries_kernel<<<cdiv(m, 256), 256, 0, s>>>((const Raw80 *)raw80_dev, (uint32_t)m,
+                                                       xyz_dev);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode,
+                      double **xyz_out, bool *representable)
+{
+    (void)coord_mode;
+    cudaStream_t s = ix->stream;
+    *xyz_out = nullptr;
+    *representable = true;
+    if (n == 0) return PT_OK;
+    double *xyz = nullptr;
+    PT_CUDA(cudaMalloc(&xyz, sizeof(double) * 3 * n));
+    PT_CUDA(cudaMalloc(&ix->attrs, sizeof(pt_attr) * n));
+    unsigned int *flag = nullptr;
+    PT_CUDA(cudaMalloc(&flag, sizeof(unsigned int)));
+    PT_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), s));
+    // chunked upload through two device staging buffers
+    const size_t chunk = (size_t)1 << 22;  // 4 Mi records = 320 MiB per buffer
+    size_t cap = n < chunk ? n : chunk;
+    Raw80 *stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    PT_CUDA(cudaMalloc(&stage[0], sizeof(Raw80) * cap));
+    PT_CUDA(cudaMalloc(&stage[1], sizeof(Raw80) * cap));
+    PT_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    PT_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    int b = 0;
+    for (size_t off = 0; off < n; off += cap, b ^= 1) {
+        size_t cnt = n - off < cap ? n - off : cap;
+        PT_CUDA(cudaEventSynchronize(done[b]));
+        PT_CUDA(cudaMemcpyAsync(stage[b], (const char *)points + off * sizeof(Raw80),
+                                cnt * sizeof(Raw80), cudaMemcpyHostToDevice, s));
+        unpack_points_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(stage[b], (uint32_t)cnt,
+                                                            xyz + 3 * off, ix->attrs + off, flag);
+        count_launch();
+        PT_CUDA(cudaEventRecord(done[b], s));
+    }
+    unsigned int h_flag = 0;
+    PT_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof h_flag, cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaStreamSynchronize(s));
+    cudaFree(stage[0]); cudaFree(stage[1]); cudaFree(flag);
+    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    *representable = h_flag == 0;
+    *xyz_out = xyz;
+    return PT_OK;
+}
+
+}  // namespace pt

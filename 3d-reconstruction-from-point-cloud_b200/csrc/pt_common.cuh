@@ -1,0 +1,117 @@
+// pt_common.cuh -- shared device/host definitions of the pointsTransfer hot path (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "points_transfer.h"
+
+namespace pt {
+
+// ---- error plumbing (nothing may throw across the C ABI) ------------------------------
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int map_cuda_error(cudaError_t e);
+#define PT_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            if (::pt::verbose())                                                   \
+                fprintf(stderr, "[points_transfer] %s:%d %s -> %s\n", __FILE__,    \
+                        __LINE__, #call, cudaGetErrorString(e__));                 \
+            return ::pt::map_cuda_error(e__);                                      \
+        }                                                                          \
+    } while (0)
+#define PT_TRY(call)                   \
+    do {                               \
+        int s__ = (call);              \
+        if (s__ != PT_OK) return s__;  \
+    } while (0)
+bool verbose();
+
+// ---- data layout in HBM -----------------------------------------------------------------
+// The cloud is stored Morton-sorted in 32-point leaves ("buckets"); one leaf is one
+// contiguous, 16-byte aligned run: 512 B (F32) or 1 KiB (F64).
+constexpr int LEAF = 32;
+
+struct PointF {          // 16 B: float4 with the local point index in .w's bits
+    float x, y, z;
+    int   idx;
+};
+struct __align__(16) PointD {  // 32 B
+    double x, y, z;
+    int    idx;
+    int    pad;
+};
+
+// Axis-aligned box of a pyramid node, float, rounded outward for F64 clouds.  32 B so a
+// lane / thread fetches it with two 16-byte loads.
+struct __align__(16) Box {
+    float lox, loy, loz, hix;
+    float hiy, hiz, pad0, pad1;
+};
+
+constexpr int MAX_PYR_LEVELS = 32;  // binary pyramid: level j covers 2^j leaves
+constexpr int WLOG = 5;             // the warp traversal is 32-wide: uses levels 0,5,10,...
+constexpr int MAX_W_LEVELS = 6;     // 32^6 leaves
+
+struct Pyramid {
+    const Box *level[MAX_PYR_LEVELS];
+    uint32_t   count[MAX_PYR_LEVELS];
+    int        n_levels;
+};
+
+struct QueryParams {
+    const void    *pts;        // PointF* or PointD*, n_pad records
+    const pt_attr *attrs;      // original (local) order, may be null
+    const int32_t *ids;        // local -> global id, may be null
+    Pyramid        pyr;
+    uint32_t       n;          // points
+    uint32_t       n_leaves;
+    int            w_levels;   // number of 32-wide levels used by the warp traversal
+    const double  *queries;    // m * 3
+    const double  *r2_per_query;
+    uint32_t       m;
+    int            k;
+    double         r2;         // squared radius bound (+inf if unbounded)
+    int32_t       *idx_out;
+    double        *d2_out;
+    uint8_t       *rgba_out;
+    float         *normal_out;
+    pt_cand       *cand_out;
+};
+
+// ---- the metric: src/Distance.h:6-11, fp64, (dx*dx + dy*dy) + dz*dz, never contracted ----
+__device__ __forceinline__ double dist2_exact(double qx, double qy, double qz, double px,
+                                              double py, double pz)
+{
+    double dx = __dsub_rn(qx, px);
+    double dy = __dsub_rn(qy, py);
+    double dz = __dsub_rn(qz, pz);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// Ordering key (d2, index): lowest index wins ties.
+__device__ __forceinline__ bool key_less(double da, int ia, double db, int ib)
+{
+    return da < db || (da == db && ia < ib);
+}
+
+constexpr int IDX_NONE = 0x7fffffff;  // sentinel index of an empty list slot
+
+// Conservative fp32 lower bound of Distance::min_distance_to_rectangle (src/Distance.h:27-57):
+// every operation rounds toward the safe side, so lb <= the real bound <= real d2 of any
+// point inside the box.  The query is bracketed by [q_dn, q_up] (fp32 round-down / round-up).
+__device__ __forceinline__ float box_lower_bound(const float qdn[3], const float qup[3],
+                                                 const Box &b)
+{
+    float ex = fmaxf(fmaxf(__fsub_rd(b.lox, qup[0]), __fsub_rd(qdn[0], b.hix)), 0.0f);
+    float ey = fmaxf(fmaxf(__fsub_rd(b.loy, qup[1]), __fsub_rd(qdn[1], b.hiy)), 0.0f);
+    float ez = fmaxf(fmaxf(__fsub_rd(b.loz, qup[2]), __fsub_rd(qdn[2], b.hiz)), 0.0f);
+    return __fadd_rd(__fadd_rd(__fmul_rd(ex, ex), __fmul_rd(ey, ey)), __fmul_rd(ez, ez));
+}
+
+}  // namespace pt

@@ -1,0 +1,79 @@
+// pt_index.cuh -- the opaque handle behind the C ABI and internal entry points.
+#pragma once
+
+#include "pt_common.cuh"
+
+struct pt_index {
+    int          device = 0;
+    int          coord_f64 = 0;
+    uint32_t     n = 0;
+    uint32_t     n_leaves = 0;
+    int          w_levels = 0;
+    void        *pts = nullptr;      // PointF/PointD [n_leaves*LEAF], Morton order
+    pt_attr     *attrs = nullptr;    // [n] original order (may be null)
+    int32_t     *ids = nullptr;      // [n] original order (may be null)
+    pt::Box     *boxes = nullptr;    // all pyramid levels, level 0 first
+    pt::Pyramid  pyr{};
+    double       bb_lo[3]{}, bb_hi[3]{};
+    uint64_t     device_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  ev[4]{};
+    float        build_ms = 0, last_query_ms = 0, last_h2d_ms = 0, last_d2h_ms = 0;
+
+    // grow-only workspaces for the host-buffer API
+    void  *ws_raw = nullptr;   size_t ws_raw_bytes = 0;    // uploaded 80-byte query records
+    void  *ws_q = nullptr;     size_t ws_q_bytes = 0;      // m*3 doubles
+    void  *ws_out = nullptr;   size_t ws_out_bytes = 0;    // idx | d2 | rgba | normal
+};
+
+namespace pt {
+
+// Input accessors for the build: where the unsorted coordinates come from.
+struct InF4 {   // n x float4 (x,y,z,unused)
+    const float4 *p;
+    __device__ __forceinline__ void load(uint32_t i, double &x, double &y, double &z) const
+    {
+        float4 v = p[i];
+        x = v.x; y = v.y; z = v.z;
+    }
+};
+struct InD4 {   // n x double4-like (x,y,z,unused), 32-byte records
+    const double *p;
+    __device__ __forceinline__ void load(uint32_t i, double &x, double &y, double &z) const
+    {
+        const double2 *q = reinterpret_cast<const double2 *>(p + 4 * (size_t)i);
+        double2 a = q[0], b = q[1];
+        x = a.x; y = a.y; z = b.x;
+    }
+};
+struct InD3 {   // n x 3 packed doubles
+    const double *p;
+    __device__ __forceinline__ void load(uint32_t i, double &x, double &y, double &z) const
+    {
+        x = p[3 * (size_t)i]; y = p[3 * (size_t)i + 1]; z = p[3 * (size_t)i + 2];
+    }
+};
+
+// Builds the sorted leaves + box pyramid into `ix` (which already holds device/stream/attrs/
+// ids).  out_f64 selects PointD storage.  Synchronises ix->stream before returning.
+int build_index_f4(pt_index *ix, const float4 *pos, uint32_t n, bool out_f64);
+int build_index_d4(pt_index *ix, const double *pos, uint32_t n, bool out_f64);
+int build_index_d3(pt_index *ix, const double *pos, uint32_t n, bool out_f64);
+
+// Upload + unpack the reference's 80-byte AoS records.
+int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode,
+                      double **xyz_out /* n*3 doubles, device, caller frees */,
+                      bool *representable);
+int unpack_queries_aos(const void *raw80_dev, size_t m, double *xyz_dev, cudaStream_t s);
+
+int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s);
+int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *idx_out,
+                 double *d2_out, uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
+                 cudaStream_t s);
+
+int  get_option(const char *name, int *value);
+int  set_option(const char *name, int value);
+int  opt_knn_variant();
+int  opt_order();
+
+}  // namespace pt

@@ -1,0 +1,162 @@
+/*
+ * points_transfer.h -- C ABI of the B200-native pointsTransfer hot path.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one call site of
+ * the reference (horizon-research/3D-Reconstruction-From-Point-Cloud, paths
+ * relative to its root):
+ *
+ *   pt_index_build   <- `Tree tree(points.begin(), points.end());`
+ *                       src/pointsTransfer.cpp:259 (typedefs :37-40); the lazy
+ *                       CGAL kd-tree build hidden in the first query as well.
+ *   pt_knn           <- `K_neighbor_search search(tree, q, K);` + the result
+ *                       iteration, src/pointsTransfer.cpp:474-478, metric
+ *                       src/Distance.h:6-11, radius transform src/Distance.h:97.
+ *   pt_transfer      <- the per-sample transfer loop src/pointsTransfer.cpp:
+ *                       465-479 + the colour blend semantics of :95-103.
+ *   pt_index_free    <- `tree` going out of scope at src/pointsTransfer.cpp:626.
+ *
+ * Records are the reference's own 80-byte AoS `struct Point`
+ * (src/Point.h:1-6): double ver[3] @0, double normal[3] @24, int color[3] @48,
+ * double U @64, double V @72.  They are passed as `const void*` so a caller can
+ * hand over `points.data()` of its `std::vector<Point>` unchanged.
+ *
+ * Contract: plain pointers and sizes only; int
+ * status returned (0 = ok), nothing thrown across the ABI; blocking -- every
+ * call is stream-synchronised on return; one handle <-> one caller thread at a
+ * time (thread-compatible); results in query order; neighbours in ascending
+ * (d2, index) order, ties broken by lowest point index; short lists padded with
+ * index -1 / d2 +inf.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point returns PT_ERR_NO_DEVICE.
+ */
+#ifndef POINTS_TRANSFER_H
+#define POINTS_TRANSFER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_OK                 0
+#define PT_ERR_INVALID_ARG    1
+#define PT_ERR_CUDA           2
+#define PT_ERR_NO_DEVICE      3
+#define PT_ERR_OUT_OF_MEMORY  4
+#define PT_ERR_UNSUPPORTED    5  /* e.g. k > PT_MAX_K */
+#define PT_ERR_NOT_REPRESENTABLE 6 /* coord_mode = PT_COORD_F32 but input is not fp32-exact */
+#define PT_ERR_NON_FINITE     7  /* NaN/inf coordinate in the cloud */
+
+#define PT_MAX_K 32
+#define PT_POINT_STRIDE 80 /* sizeof(struct Point), src/Point.h */
+
+/* Coordinate storage of the index.  The metric is always evaluated in fp64 in
+ * the reference's operation order (src/Distance.h:6-11).  F32 storage (16-byte
+ * float4 records) is lossless only when every cloud coordinate is exactly
+ * representable in fp32; AUTO checks that on the device and falls back to the
+ * 32-byte fp64 records otherwise, so neighbour indices stay bit-exact. */
+#define PT_COORD_AUTO 0
+#define PT_COORD_F32  1
+#define PT_COORD_F64  2
+
+typedef struct pt_index pt_index; /* opaque; owns device memory + one stream */
+
+typedef struct pt_build_opts {
+    int device;            /* CUDA ordinal; -1 = current device */
+    int coord_mode;        /* PT_COORD_* */
+    const int32_t *ids;    /* optional n global point ids, strictly increasing
+                              (slab of a sharded cloud); NULL => 0..n-1 */
+    int reserved[8];       /* must be zero */
+} pt_build_opts;
+
+typedef struct pt_index_info {
+    uint64_t n_points;
+    uint64_t n_leaves;       /* 32-point buckets of the Morton-sorted cloud */
+    int      n_levels;       /* box-pyramid levels */
+    int      coord_mode;     /* PT_COORD_F32 or PT_COORD_F64 actually used */
+    int      device;
+    int      reserved_;
+    double   bbox_lo[3], bbox_hi[3];
+    uint64_t device_bytes;   /* resident after the build */
+    float    build_ms;       /* device time of the last build (CUDA events) */
+    float    last_query_ms;  /* device time of the last pt_knn/pt_transfer kernels */
+    float    last_h2d_ms, last_d2h_ms;
+} pt_index_info;
+
+/* Library / device probing (no compute). */
+const char *pt_version(void);
+const char *pt_status_string(int status);
+int         pt_device_count(void); /* 0 when no CUDA device/driver */
+
+/* Host-buffer API: the reference-facing plugin surface. ------------------- */
+
+int pt_index_build(const void *points, size_t n, const pt_build_opts *opts,
+                   pt_index **out);
+int pt_index_free(pt_index *index);
+int pt_index_get_info(const pt_index *index, pt_index_info *info);
+
+/* radius < 0 or +inf: unbounded k-NN (the reference's mode).  Otherwise only
+ * points with d2 <= Distance::transformed_distance(radius) (src/Distance.h:97).
+ * idx_out[m*k] (int32), d2_out[m*k] (double, may be NULL). */
+int pt_knn(pt_index *index, const void *queries, size_t m, int k, double radius,
+           int32_t *idx_out, double *d2_out);
+
+/* k-NN + fused distance-weighted colour/normal blend (DESIGN.md "blend").
+ * idx_out / d2_out may be NULL; rgba_out[m*4] (r,g,b,255), normal_out[m*3]. */
+int pt_transfer(pt_index *index, const void *queries, size_t m, int k,
+                double radius, int32_t *idx_out, double *d2_out,
+                uint8_t *rgba_out, float *normal_out);
+
+/* Device-buffer API: same operations with inputs/outputs already resident in
+ * HBM on the index's device (bench `value`, multi-GPU slabs).  `stream` is a
+ * cudaStream_t passed as void* (NULL = the index's own stream); these calls
+ * are asynchronous with respect to the host unless stated. -------------- */
+
+/* 16-byte point attribute record kept in original point order. */
+typedef struct pt_attr {
+    float   nx, ny, nz;
+    uint8_t r, g, b, a;
+} pt_attr;
+
+/* 32-byte candidate record exchanged between slabs (NCCL payload). */
+typedef struct pt_cand {
+    double  d2;      /* +inf when empty */
+    int32_t id;      /* global point id, -1 when empty */
+    uint8_t r, g, b, a;
+    float   nx, ny, nz;
+    int32_t pad_;
+} pt_cand;
+
+/* pos: n records of 4 floats (x,y,z,unused) when coord_f64 == 0, or 4 doubles
+ * (x,y,z,unused) when coord_f64 != 0.  attrs may be NULL (no blend possible).
+ * ids as in pt_build_opts (device pointer).  Synchronises before returning. */
+int pt_index_build_device(const void *pos, int coord_f64, const pt_attr *attrs,
+                          const int32_t *ids, size_t n, int device,
+                          pt_index **out);
+
+/* queries_xyz: m*3 doubles.  Any output pointer may be NULL.  cand_out[m*k]
+ * receives the per-slab candidate lists for the multi-GPU merge.
+ * radius2_per_query (may be NULL): per-query squared search bound that
+ * overrides `radius` (used for halo searches bounded by the owner's k-th d2;
+ * a candidate must have d2 <= bound). */
+int pt_query_device(pt_index *index, const double *queries_xyz, size_t m, int k,
+                    double radius, const double *radius2_per_query,
+                    int32_t *idx_out, double *d2_out, uint8_t *rgba_out,
+                    float *normal_out, pt_cand *cand_out, void *stream);
+
+/* K5: merge n_lists candidate lists per query (lists[l*m*k + q*k + j], each
+ * ascending, padded) into the global top-k and blend.  Runs on `device`. */
+int pt_merge_device(const pt_cand *lists, int n_lists, size_t m, int k,
+                    int32_t *idx_out, double *d2_out, uint8_t *rgba_out,
+                    float *normal_out, pt_cand *cand_out, int device, void *stream);
+
+/* Tuning / introspection. */
+int pt_set_option(const char *name, int value); /* e.g. "knn_variant" */
+int pt_get_option(const char *name, int *value);
+/* Number of kernels this library launched since process start (gpu_launches). */
+uint64_t pt_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTS_TRANSFER_H */

@@ -172,6 +172,8 @@ int pto_blend(const pto_point *pts, int64_t n, int64_t m, int k,
               float *normal_out)
 {
     if (k <= 0 || k > PTO_SLOTS) return 1;
+    int bad_index = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad_index)
     for (int64_t q = 0; q < m; ++q) {
         const int32_t *qi = idx + q * k;
         const double *qd = d2 + q * k;
@@ -185,9 +187,9 @@ int pto_blend(const pto_point *pts, int64_t n, int64_t m, int k,
             continue;
         }
         double w[PTO_SLOTS];
-        int mode = 0; /* 0: 1/d2, 1: exact hits only, 2: nearest only */
+        /* 0: 1/d2, 1: exact hits only (d2 == 0), 2: nearest only (weights overflowed) */
+        int mode = (qd[0] == 0.0) ? 1 : 0;
         for (int pass = 0; pass < 2; ++pass) {
-            if (qd[0] == 0.0) mode = 1;
             for (int j = 0; j < PTO_SLOTS; ++j) {
                 if (j >= cnt) w[j] = 0.0;
                 else if (mode == 0) w[j] = 1.0 / qd[j];
@@ -203,8 +205,8 @@ int pto_blend(const pto_point *pts, int64_t n, int64_t m, int k,
         double acc[7][PTO_SLOTS];
         for (int j = 0; j < PTO_SLOTS; ++j) {
             if (j < cnt) {
-                if (qi[j] >= n) return 3;
-                const pto_point *p = &pts[qi[j]];
+                if (qi[j] >= n) bad_index = 1;
+                const pto_point *p = &pts[qi[j] >= n ? 0 : qi[j]];
                 acc[0][j] = w[j];
                 for (int c = 0; c < 3; ++c) {
                     int col = p->color[c];
@@ -233,7 +235,7 @@ int pto_blend(const pto_point *pts, int64_t n, int64_t m, int k,
             nrm[0] = nrm[1] = nrm[2] = 0.0f;
         }
     }
-    return 0;
+    return bad_index ? 3 : 0;
 }
 
 /* ---- kd-tree: CGAL Kd_tree<Sliding_midpoint, bucket 10> (recalled) ------- */

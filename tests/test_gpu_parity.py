@@ -1,0 +1,260 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): neighbour indices and squared distances bit-exact (ties ->
+lowest point index); blended colours exact, normals within 1e-5 relative.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(
+    os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+NORMAL_RTOL = 1e-5   # tolerance stated by north_star for transferred normals
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    return torch
+
+
+def _check_blend(got_rgba, got_nrm, ref_rgba, ref_nrm):
+    assert np.array_equal(got_rgba, ref_rgba)
+    assert np.allclose(got_nrm, ref_nrm, rtol=NORMAL_RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_fixtures(name, pkg, golden_dir, torch_cuda):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    P = pkg.make_points(z["xyz"], normal=z["normal"], color=z["color"])
+    Q = pkg.make_points(z["queries"])
+    radius = float(z["radius"])
+    with pkg.Tree(P) as tree:
+        expect_f64 = not np.array_equal(z["xyz"].astype(np.float32).astype(np.float64), z["xyz"])
+        assert tree.info().coord_mode == (pkg.COORD_F64 if expect_f64 else pkg.COORD_F32)
+        for k in z["ks"]:
+            k = int(k)
+            idx, d2 = tree.knn(Q, k, radius=radius)
+            assert np.array_equal(idx, z[f"idx_k{k}"]), f"{name} k={k}: indices"
+            assert np.array_equal(d2, z[f"d2_k{k}"]), f"{name} k={k}: d2"
+            out = tree.transfer(Q, k, radius=radius, want_idx=True, want_d2=True)
+            assert np.array_equal(out["idx"], idx) and np.array_equal(out["d2"], d2)
+            _check_blend(out["rgba"], out["normal"], z[f"rgba_k{k}"], z[f"normal_k{k}"])
+
+
+def test_f64_storage_forced_and_f32_rejected(pkg, pto, torch_cuda):
+    rng = np.random.default_rng(5)
+    xyz = rng.random((3000, 3))          # not fp32-representable
+    P, Q = pkg.make_points(xyz), pkg.make_points(rng.random((100, 3)))
+    with pytest.raises(pkg.PointsTransferError) as e:
+        pkg.Tree(P, coord_mode=pkg.COORD_F32)
+    assert e.value.status == 6
+    ref_idx, ref_d2 = pto.knn_bruteforce(P, Q, 20)
+    for mode in (pkg.COORD_AUTO, pkg.COORD_F64):
+        with pkg.Tree(P, coord_mode=mode) as t:
+            idx, d2 = t.knn(Q, 20)
+        assert np.array_equal(idx, ref_idx) and np.array_equal(d2, ref_d2)
+    # representable data stored as fp64 on request gives the same answer
+    P32 = pkg.make_points(xyz.astype(np.float32))
+    ref_idx, ref_d2 = pto.knn_bruteforce(P32, Q, 8)
+    for mode in (pkg.COORD_F32, pkg.COORD_F64):
+        with pkg.Tree(P32, coord_mode=mode) as t:
+            idx, d2 = t.knn(Q, 8)
+        assert np.array_equal(idx, ref_idx) and np.array_equal(d2, ref_d2)
+
+
+@pytest.mark.parametrize("k", [1, 8, 16, 20, 32])
+def test_surface_cloud_vs_kdtree_oracle(k, pkg, pto, torch_cuda):
+    # config-1 shaped (SURVEY 8 M1), sized so the oracle finishes in seconds
+    P = pkg.synth.cloud_host(300_000, seed=100 + k, side=80.0)
+    V = pkg.synth.samples_host(70, side=80.0)
+    ref_idx, ref_d2 = pto.KdTree(P).knn(V, k, exact_ties=True)
+    ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+    with pkg.Tree(P) as tree:
+        out = tree.transfer(V, k, want_idx=True, want_d2=True)
+    assert np.array_equal(out["idx"], ref_idx)
+    assert np.array_equal(out["d2"], ref_d2)
+    _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
+
+
+def test_reference_call_site_shape(pkg, pto, torch_cuda):
+    # src/pointsTransfer.cpp:470-479: per face, per corner, K=20 search; iterate (point, d2)
+    P = pkg.synth.cloud_host(20_000, seed=9, side=20.0)
+    V = pkg.synth.samples_host(6, side=20.0)
+    F = pkg.synth.grid_faces(6, 6)
+    K = 20
+    ref_idx, ref_d2 = pto.knn_bruteforce(P, V, K)
+    with pkg.Tree(P) as tree:
+        for j in (0, 7, F.shape[0] - 1):
+            for i in range(3):
+                v = int(F[j, i])
+                search = pkg.K_neighbor_search(tree, V[v], K)
+                got = list(search)
+                assert len(search) == K
+                assert [g[0] for g in got] == ref_idx[v].tolist()
+                assert [g[1] for g in got] == ref_d2[v].tolist()
+
+
+def test_device_api_ids_and_radius_per_query(pkg, pto, torch_cuda):
+    torch = torch_cuda
+    rng = np.random.default_rng(21)
+    n, m, k = 50_000, 2_000, 16
+    xyz = (rng.random((n, 3)) * 30).astype(np.float32)
+    P = pkg.make_points(xyz, normal=rng.standard_normal((n, 3)).astype(np.float32),
+                        color=rng.integers(0, 256, (n, 3)))
+    qxyz = (rng.random((m, 3)) * 30).astype(np.float32).astype(np.float64)
+    Q = pkg.make_points(qxyz)
+    ids = np.cumsum(rng.integers(1, 4, n)).astype(np.int32)   # strictly increasing global ids
+    pos = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    pos[:, :3] = torch.from_numpy(xyz).cuda()
+    attrs = np.zeros(n, dtype=pkg.ATTR_DTYPE)
+    attrs["nx"], attrs["ny"], attrs["nz"] = P["normal"][:, 0], P["normal"][:, 1], P["normal"][:, 2]
+    attrs["rgba"][:, :3] = P["color"]
+    attrs["rgba"][:, 3] = 255
+    t_attrs = torch.from_numpy(attrs.view(np.uint8).reshape(n, 16)).cuda()
+    tree = pkg.DeviceTree(pos, t_attrs, torch.from_numpy(ids).cuda())
+    tq = torch.from_numpy(qxyz).cuda()
+    idx = torch.empty((m, k), dtype=torch.int32, device="cuda")
+    d2 = torch.empty((m, k), dtype=torch.float64, device="cuda")
+    rgba = torch.empty((m, 4), dtype=torch.uint8, device="cuda")
+    nrm = torch.empty((m, 3), dtype=torch.float32, device="cuda")
+    tree.query(tq, k, idx=idx, d2=d2, rgba=rgba, normal=nrm)
+    torch.cuda.synchronize()
+    ref_idx, ref_d2 = pto.knn_bruteforce(P, Q, k)
+    assert np.array_equal(idx.cpu().numpy(), np.where(ref_idx >= 0, ids[ref_idx], -1))
+    assert np.array_equal(d2.cpu().numpy(), ref_d2)
+    ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+    _check_blend(rgba.cpu().numpy(), nrm.cpu().numpy(), ref_rgba, ref_nrm)
+    # per-query squared bound: bound = the 5th neighbour's d2 -> exactly 5 results (no ties here)
+    r2 = torch.from_numpy(ref_d2[:, 4].copy()).cuda()
+    tree.query(tq, k, radius2_per_query=r2, idx=idx, d2=d2)
+    torch.cuda.synchronize()
+    got = idx.cpu().numpy()
+    assert np.array_equal(got[:, :5], ids[ref_idx[:, :5]]) and np.all(got[:, 5:] == -1)
+    tree.close()
+
+
+@pytest.mark.parametrize("n_slabs,k", [(2, 8), (3, 16), (8, 32)])
+def test_slab_merge_equals_single_index(n_slabs, k, pkg, pto, torch_cuda):
+    """SURVEY 8(e): R slabs on one GPU, per-slab top-k, merged by the K5 kernel, must be
+    bit-identical to the single-index result."""
+    torch = torch_cuda
+    P = pkg.synth.cloud_host(120_000, seed=33, side=60.0)
+    V = pkg.synth.samples_host(40, side=60.0)
+    m = V.shape[0]
+    ref_idx, ref_d2 = pto.KdTree(P).knn(V, k)
+    ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+    order = np.argsort(P["ver"][:, 0], kind="stable")
+    bounds = np.linspace(0, len(P), n_slabs + 1).astype(int)
+    tq = torch.from_numpy(np.ascontiguousarray(V["ver"])).cuda()
+    lists = torch.empty((n_slabs, m, k, 32), dtype=torch.uint8, device="cuda")
+    trees = []
+    for s in range(n_slabs):
+        ids = np.sort(order[bounds[s]:bounds[s + 1]]).astype(np.int32)   # increasing global ids
+        sub = P[ids]
+        pos = torch.zeros((len(ids), 4), dtype=torch.float32, device="cuda")
+        pos[:, :3] = torch.from_numpy(sub["ver"].astype(np.float32)).cuda()
+        attrs = np.zeros(len(ids), dtype=pkg.ATTR_DTYPE)
+        attrs["nx"], attrs["ny"], attrs["nz"] = sub["normal"][:, 0], sub["normal"][:, 1], sub["normal"][:, 2]
+        attrs["rgba"][:, :3] = sub["color"]
+        attrs["rgba"][:, 3] = 255
+        t = pkg.DeviceTree(pos, torch.from_numpy(attrs.view(np.uint8).reshape(-1, 16)).cuda(),
+                           torch.from_numpy(ids).cuda())
+        t.query(tq, k, cand=lists[s].view(-1))
+        trees.append(t)
+    idx = torch.empty((m, k), dtype=torch.int32, device="cuda")
+    d2 = torch.empty((m, k), dtype=torch.float64, device="cuda")
+    rgba = torch.empty((m, 4), dtype=torch.uint8, device="cuda")
+    nrm = torch.empty((m, 3), dtype=torch.float32, device="cuda")
+    pkg.merge_device(lists.view(-1), n_slabs, m, k, idx=idx, d2=d2, rgba=rgba, normal=nrm)
+    torch.cuda.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert np.array_equal(d2.cpu().numpy(), ref_d2)
+    _check_blend(rgba.cpu().numpy(), nrm.cpu().numpy(), ref_rgba, ref_nrm)
+    for t in trees:
+        t.close()
+
+
+def test_edge_cases(pkg, torch_cuda):
+    empty = np.zeros(0, dtype=pkg.POINT_DTYPE)
+    Q = pkg.make_points(np.zeros((3, 3)))
+    with pkg.Tree(empty) as t:                       # empty cloud
+        idx, d2 = t.knn(Q, 4)
+        assert np.all(idx == -1) and np.all(np.isinf(d2))
+        out = t.transfer(Q, 4)
+        assert not out["rgba"].any() and not out["normal"].any()
+    one = pkg.make_points(np.array([[1.0, 2.0, 3.0]]), color=[[7, 8, 9]], normal=[[0, 0, 2.0]])
+    with pkg.Tree(one) as t:                         # single point, zero queries, k limits
+        idx, d2 = t.knn(Q, 3)
+        assert idx.tolist() == [[0, -1, -1]] * 3 and np.all(d2[:, 0] == 14.0)
+        out = t.transfer(Q, 3)
+        assert out["rgba"].tolist() == [[7, 8, 9, 255]] * 3
+        assert np.allclose(out["normal"], [[0, 0, 1.0]] * 3)
+        i0, _ = t.knn(empty, 3)
+        assert i0.shape == (0, 3)
+        for bad_k in (0, 33):
+            with pytest.raises(pkg.PointsTransferError) as e:
+                t.knn(Q, bad_k)
+            assert e.value.status == 5
+    bad = pkg.make_points(np.array([[0.0, np.nan, 0.0], [1.0, 1.0, 1.0]]))
+    with pytest.raises(pkg.PointsTransferError) as e:
+        pkg.Tree(bad)
+    assert e.value.status == 7
+
+
+def test_full_size_properties(pkg, pto, torch_cuda):
+    """BASELINE config 2 at full size (50M points, 200k samples, k=16): size-independent
+    properties + exact verification of sampled queries by restriction (every true neighbour of
+    a sample lies within its reported k-th distance, so the oracle on that ball must agree)."""
+    torch = torch_cuda
+    w = pkg.synth.CONFIGS["cfg2"]
+    free, _ = torch.cuda.mem_get_info()
+    n = w.n_points if free > 24e9 else 5_000_000
+    pos, attrs = pkg.synth.cloud_device(n, w.seed)
+    q = pkg.synth.samples_device(w.gu, w.gv)
+    m, k = q.shape[0], w.k
+    tree = pkg.DeviceTree(pos, attrs)
+    idx = torch.empty((m, k), dtype=torch.int32, device="cuda")
+    d2 = torch.empty((m, k), dtype=torch.float64, device="cuda")
+    rgba = torch.empty((m, 4), dtype=torch.uint8, device="cuda")
+    nrm = torch.empty((m, 3), dtype=torch.float32, device="cuda")
+    tree.query(q, k, idx=idx, d2=d2, rgba=rgba, normal=nrm)
+    torch.cuda.synchronize()
+    # sortedness, uniqueness, full lists
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())
+    assert bool((idx >= 0).all()) and bool((idx < n).all())
+    srt = idx.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    # reported d2 equals the metric recomputed from the coordinates (torch fp64, same op order)
+    p = pos[idx.long().view(-1), :3].double().view(m, k, 3)
+    diff = q.view(m, 1, 3) - p
+    sq = diff * diff
+    assert bool((((sq[..., 0] + sq[..., 1]) + sq[..., 2]) == d2).all())
+    # idempotence: a second pass gives identical bits
+    idx2 = torch.empty_like(idx)
+    tree.query(q, k, idx=idx2)
+    torch.cuda.synchronize()
+    assert bool((idx2 == idx).all())
+    # unit normals, opaque alpha
+    nn = nrm.double().norm(dim=1)
+    assert bool(((nn - 1).abs() < 1e-5).all()) and bool((rgba[:, 3] == 255).all())
+    # exact check of sampled queries by restriction to the k-th-distance ball
+    sel = np.linspace(0, m - 1, 48).astype(int)
+    pos64 = pos[:, :3].double()
+    for s in sel:
+        r2 = float(d2[s, k - 1])
+        dd = ((pos64 - q[s]) ** 2).sum(1)
+        cand = torch.nonzero(dd <= r2 * (1 + 1e-9)).view(-1)
+        ids = cand.cpu().numpy().astype(np.int32)          # ascending
+        sub = pkg.make_points(pos[cand, :3].cpu().numpy().astype(np.float64))
+        ridx, rd2 = pto.knn_bruteforce(sub, pkg.make_points(q[s].cpu().numpy()[None]), k)
+        assert np.array_equal(ids[ridx[0]], idx[s].cpu().numpy())
+        assert np.array_equal(rd2[0], d2[s].cpu().numpy())
+    tree.close()
