@@ -12,8 +12,8 @@ namespace pt {
 
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_verbose{-1};
-static std::atomic<int> g_knn_variant{0};
-static std::atomic<int> g_order{0};
+static std::atomic<int> g_knn_variant{1};
+static std::atomic<int> g_order{1};
 
 bool verbose()
 {
@@ -93,7 +93,7 @@ static void destroy_index(pt_index *ix)
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     cudaFree(ix->pts); cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->boxes);
-    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out);
+    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf);
     for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -114,6 +114,7 @@ static void fill_params(const pt_index *ix, QueryParams &qp)
     qp.n = ix->n;
     qp.n_leaves = ix->n_leaves;
     qp.w_levels = ix->w_levels;
+    qp.t_levels = ix->t_levels;
 }
 
 }  // namespace pt
@@ -251,7 +252,7 @@ int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, do
     qp.r2 = radius_to_r2(radius);
     qp.idx_out = idx_out; qp.d2_out = d2_out; qp.rgba_out = rgba_out;
     qp.normal_out = normal_out; qp.cand_out = cand_out;
-    return launch_query(ix, qp, stream ? (cudaStream_t)stream : ix->stream);
+    return launch_query(ix, qp, (cudaStream_t)stream);
 }
 
 int pt_merge_device(const pt_cand *lists, int n_lists, size_t m, int k, int32_t *idx_out,
@@ -292,7 +293,7 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
                              idx_out ? (int32_t *)(o + off_idx) : nullptr,
                              d2_out ? (double *)(o + off_d2) : nullptr,
                              rgba_out ? (uint8_t *)(o + off_rgba) : nullptr,
-                             normal_out ? (float *)(o + off_nrm) : nullptr, nullptr, s);
+                             normal_out ? (float *)(o + off_nrm) : nullptr, nullptr, (void *)s);
     if (rc != PT_OK) return rc;
     PT_CUDA(cudaEventRecord(ix->ev[2], s));
     if (d2_out) PT_CUDA(cudaMemcpyAsync(d2_out, o + off_d2, mk * 8, cudaMemcpyDeviceToHost, s));

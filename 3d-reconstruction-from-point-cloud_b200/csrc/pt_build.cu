@@ -84,9 +84,34 @@ __device__ __forceinline__ unsigned long long spread21(unsigned int v)
     return x;
 }
 
+// 3-D Hilbert index of 21-bit cell coordinates (Skilling's transpose algorithm): consecutive
+// keys are always face-adjacent cells, so 32-point runs make tighter leaves than Morton order.
+__device__ __forceinline__ unsigned long long hilbert63(unsigned int x, unsigned int y,
+                                                        unsigned int z)
+{
+    unsigned int X[3] = {x, y, z};
+    const unsigned int M = 1u << 20;
+    for (unsigned int Q = M; Q > 1; Q >>= 1) {
+        const unsigned int Pm = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) X[0] ^= Pm;
+            else { unsigned int t = (X[0] ^ X[i]) & Pm; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    unsigned int t = 0;
+    for (unsigned int Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (spread21(X[0]) << 2) | (spread21(X[1]) << 1) | spread21(X[2]);
+}
+
 struct KeyParams {
     double lo[3];
     double inv_cell;   // 2^21 / max extent (0 when the cloud is a single point)
+    int    order;      // 0 = Morton, 1 = Hilbert
 };
 
 template <typename In>
@@ -104,7 +129,8 @@ __global__ void __launch_bounds__(256) morton_kernel(In in, uint32_t n, KeyParam
         t = fmin(fmax(t, 0.0), 2097151.0);
         c[a] = (unsigned int)t;
     }
-    keys[i] = spread21(c[0]) | (spread21(c[1]) << 1) | (spread21(c[2]) << 2);
+    keys[i] = kp.order == 1 ? hilbert63(c[0], c[1], c[2])
+                            : (spread21(c[0]) | (spread21(c[1]) << 1) | (spread21(c[2]) << 2));
     vals[i] = i;
 }
 
@@ -213,6 +239,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     for (int a = 0; a < 3; ++a) { ix->bb_lo[a] = 0; ix->bb_hi[a] = 0; }
     ix->pyr = Pyramid{};
     ix->w_levels = 0;
+    ix->t_levels = 0;
     if (n == 0) { ix->build_ms = 0; return PT_OK; }
 
     // K1: bbox
@@ -241,6 +268,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     }
     kp.inv_cell = ext > 0 ? 2097152.0 / ext : 0.0;
     if (!std::isfinite(kp.inv_cell)) kp.inv_cell = 0.0;
+    kp.order = opt_order();
 
     // K1: keys, K2: sort
     unsigned long long *keys = nullptr, *keys_alt = nullptr;
@@ -297,6 +325,9 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     int t = 1;
     for (uint64_t cap = 32; cap < ix->n_leaves; cap *= 32) ++t;
     ix->w_levels = t;
+    t = 1;
+    for (uint64_t cap = 8; cap < ix->n_leaves; cap *= 8) ++t;
+    ix->t_levels = t;
 
     PT_CUDA(cudaEventRecord(ix->ev[1], s));
     PT_CUDA(cudaStreamSynchronize(s));

@@ -72,6 +72,7 @@ struct QueryParams {
     uint32_t       n;          // points
     uint32_t       n_leaves;
     int            w_levels;   // number of 32-wide levels used by the warp traversal
+    int            t_levels;   // number of 8-wide levels used by the thread traversal
     const double  *queries;    // m * 3
     const double  *r2_per_query;
     uint32_t       m;

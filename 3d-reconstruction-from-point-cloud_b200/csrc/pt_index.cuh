@@ -9,6 +9,7 @@ struct pt_index {
     uint32_t     n = 0;
     uint32_t     n_leaves = 0;
     int          w_levels = 0;
+    int          t_levels = 0;
     void        *pts = nullptr;      // PointF/PointD [n_leaves*LEAF], Morton order
     pt_attr     *attrs = nullptr;    // [n] original order (may be null)
     int32_t     *ids = nullptr;      // [n] original order (may be null)
@@ -24,6 +25,7 @@ struct pt_index {
     void  *ws_raw = nullptr;   size_t ws_raw_bytes = 0;    // uploaded 80-byte query records
     void  *ws_q = nullptr;     size_t ws_q_bytes = 0;      // m*3 doubles
     void  *ws_out = nullptr;   size_t ws_out_bytes = 0;    // idx | d2 | rgba | normal
+    void  *ws_ovf = nullptr;   size_t ws_ovf_bytes = 0;    // queue-overflow count + sample list
 };
 
 namespace pt {

@@ -2,87 +2,45 @@
 // `K_neighbor_search search(tree, q, K)` loop, /root/reference src/pointsTransfer.cpp:470-479,
 // metric src/Distance.h:6-11, pruning bound src/Distance.h:27-57).
 //
-// Variant 0 ("warp"): one warp per sample.  The warp walks the 32-wide levels of the box
-// pyramid nearest-child-first; each lane tests one child box (conservative fp32 bound) or
-// evaluates one point of a 32-point leaf (exact fp64 metric).  The running top-k is a sorted
-// list distributed one entry per lane, so k <= 32.
+// Variant 1 ("thread", default): one thread per sample.  Best-first traversal of the 8-wide
+// levels of the box pyramid with a private priority queue (local memory) ordered by the
+// conservative fp32 box bound; leaves are scanned with the exact fp64 metric into a private
+// bounded max-heap (shared memory, one column per thread).  Samples whose queue overflows are
+// re-run by the warp kernel.
+// Variant 0 ("warp"): one warp per sample, 32-wide levels, nearest-child-first DFS, running
+// top-k as a sorted list distributed one entry per lane.  Slower (instruction bound on the
+// serial list insertions) but has no per-sample state limits: it is the overflow fallback.
 #include "pt_index.cuh"
 
 namespace pt {
 
-// ---- warp-distributed sorted list ---------------------------------------------------------
-struct WarpList {
-    double d;     // lane j holds the j-th best (ascending); +inf when empty
-    int    i;     // local point index; IDX_NONE when empty
-    double kd;    // replicated: current k-th entry (the acceptance threshold)
-    int    ki;
-};
-
-__device__ __forceinline__ double shfl_f64(double v, int src)
-{
-    return __shfl_sync(0xffffffffu, v, src);
-}
-
-// Offer one candidate per lane (pass = lane has a candidate that beats the k-th entry).
-__device__ __forceinline__ void warp_list_offer(WarpList &L, int k, unsigned lane, bool pass,
-                                                double d, int idx)
-{
-    unsigned m = __ballot_sync(0xffffffffu, pass);
-    while (m) {
-        int c = __ffs(m) - 1;
-        m &= m - 1;
-        double cd = shfl_f64(d, c);
-        int ci = __shfl_sync(0xffffffffu, idx, c);
-        if (!key_less(cd, ci, L.kd, L.ki)) continue;  // threshold moved since the ballot
-        unsigned before = __ballot_sync(0xffffffffu, key_less(L.d, L.i, cd, ci));
-        unsigned pos = __popc(before);
-        double ud = __shfl_up_sync(0xffffffffu, L.d, 1);
-        int ui = __shfl_up_sync(0xffffffffu, L.i, 1);
-        if (lane > pos) { L.d = ud; L.i = ui; }
-        else if (lane == pos) { L.d = cd; L.i = ci; }
-        L.kd = shfl_f64(L.d, k - 1);
-        L.ki = __shfl_sync(0xffffffffu, L.i, k - 1);
-    }
-}
-
-// ---- fused blend (frozen definition, DESIGN.md "blend") -------
-__device__ __forceinline__ double butterfly_sum(double v)
-{
+// ---- blend (frozen definition, DESIGN.md "blend") --------------------------------------------
+// weights 1/d2 (exact hits: only d2 == 0 neighbours, weight 1); sums accumulated sequentially
+// in neighbour order, fp64, never contracted; colour truncated, normal normalised -> fp32.
+struct BlendAcc {
+    double s[7];
+    __device__ __forceinline__ void reset()
+    {
 #pragma unroll
-    for (int s = 1; s < 32; s <<= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, s));
-    return v;
-}
-
-// Lane j holds neighbour j (has = valid), its d2 and attribute record.
-__device__ __forceinline__ void blend_store(unsigned lane, bool has, double d2, pt_attr at,
-                                            uint8_t *rgba_out, float *normal_out)
-{
-    unsigned any = __ballot_sync(0xffffffffu, has);
-    if (any == 0) {
-        if (lane < 4 && rgba_out) rgba_out[lane] = 0;
-        if (lane < 3 && normal_out) normal_out[lane] = 0.0f;
-        return;
+        for (int a = 0; a < 7; ++a) s[a] = 0.0;
     }
-    double d0 = shfl_f64(d2, 0);
-    bool exact = d0 == 0.0;
-    double w = 0.0;
-    if (has) w = exact ? (d2 == 0.0 ? 1.0 : 0.0) : __ddiv_rn(1.0, d2);
-    double W = butterfly_sum(w);
-    if (!(W > 0.0 && W < INFINITY)) {  // overflowed weights: nearest neighbour only
-        w = (lane == 0) ? 1.0 : 0.0;
-        W = butterfly_sum(w);
+    __device__ __forceinline__ void add(double w, uint32_t rgba, float nx, float ny, float nz)
+    {
+        s[0] = __dadd_rn(s[0], w);
+        s[1] = __dadd_rn(s[1], __dmul_rn(w, (double)(rgba & 0xffu)));
+        s[2] = __dadd_rn(s[2], __dmul_rn(w, (double)((rgba >> 8) & 0xffu)));
+        s[3] = __dadd_rn(s[3], __dmul_rn(w, (double)((rgba >> 16) & 0xffu)));
+        s[4] = __dadd_rn(s[4], __dmul_rn(w, (double)nx));
+        s[5] = __dadd_rn(s[5], __dmul_rn(w, (double)ny));
+        s[6] = __dadd_rn(s[6], __dmul_rn(w, (double)nz));
     }
-    double cr = butterfly_sum(__dmul_rn(w, (double)at.r));
-    double cg = butterfly_sum(__dmul_rn(w, (double)at.g));
-    double cb = butterfly_sum(__dmul_rn(w, (double)at.b));
-    double sx = butterfly_sum(__dmul_rn(w, (double)at.nx));
-    double sy = butterfly_sum(__dmul_rn(w, (double)at.ny));
-    double sz = butterfly_sum(__dmul_rn(w, (double)at.nz));
-    if (lane == 0) {
+    __device__ __forceinline__ bool weight_ok() const { return s[0] > 0.0 && s[0] < INFINITY; }
+    __device__ __forceinline__ void store(uint8_t *rgba_out, float *normal_out) const
+    {
         if (rgba_out) {
-            int r = __double2int_rz(__ddiv_rn(cr, W));
-            int g = __double2int_rz(__ddiv_rn(cg, W));
-            int b = __double2int_rz(__ddiv_rn(cb, W));
+            int r = __double2int_rz(__ddiv_rn(s[1], s[0]));
+            int g = __double2int_rz(__ddiv_rn(s[2], s[0]));
+            int b = __double2int_rz(__ddiv_rn(s[3], s[0]));
             uchar4 o;
             o.x = (unsigned char)min(max(r, 0), 255);
             o.y = (unsigned char)min(max(g, 0), 255);
@@ -91,66 +49,56 @@ __device__ __forceinline__ void blend_store(unsigned lane, bool has, double d2, 
             *reinterpret_cast<uchar4 *>(rgba_out) = o;
         }
         if (normal_out) {
-            double len = __dsqrt_rn(
-                __dadd_rn(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)), __dmul_rn(sz, sz)));
+            double len = __dsqrt_rn(__dadd_rn(
+                __dadd_rn(__dmul_rn(s[4], s[4]), __dmul_rn(s[5], s[5])), __dmul_rn(s[6], s[6])));
             if (len > 0.0 && len < INFINITY) {
-                normal_out[0] = __double2float_rn(__ddiv_rn(sx, len));
-                normal_out[1] = __double2float_rn(__ddiv_rn(sy, len));
-                normal_out[2] = __double2float_rn(__ddiv_rn(sz, len));
+                normal_out[0] = __double2float_rn(__ddiv_rn(s[4], len));
+                normal_out[1] = __double2float_rn(__ddiv_rn(s[5], len));
+                normal_out[2] = __double2float_rn(__ddiv_rn(s[6], len));
             } else {
                 normal_out[0] = normal_out[1] = normal_out[2] = 0.0f;
             }
         }
     }
-}
+};
 
-__device__ __forceinline__ pt_attr zero_attr()
+__device__ __forceinline__ double blend_weight(int mode, double d2, int j)
 {
-    pt_attr a;
-    a.nx = a.ny = a.nz = 0.f;
-    a.r = a.g = a.b = a.a = 0;
-    return a;
+    if (mode == 0) return __ddiv_rn(1.0, d2);
+    if (mode == 1) return d2 == 0.0 ? 1.0 : 0.0;
+    return j == 0 ? 1.0 : 0.0;
 }
 
-__device__ __forceinline__ pt_attr load_attr(const pt_attr *p)
+__device__ __forceinline__ void store_empty_blend(uint8_t *rgba_out, float *normal_out)
+{
+    if (rgba_out) *reinterpret_cast<uchar4 *>(rgba_out) = make_uchar4(0, 0, 0, 0);
+    if (normal_out) normal_out[0] = normal_out[1] = normal_out[2] = 0.0f;
+}
+
+struct AttrRaw {   // pt_attr as loaded: 3 floats + packed rgba
+    float nx, ny, nz;
+    uint32_t rgba;
+};
+__device__ __forceinline__ AttrRaw load_attr(const pt_attr *p)
 {
     int4 v = __ldg(reinterpret_cast<const int4 *>(p));
-    pt_attr a;
+    AttrRaw a;
     a.nx = __int_as_float(v.x); a.ny = __int_as_float(v.y); a.nz = __int_as_float(v.z);
-    a.r = v.w & 0xff; a.g = (v.w >> 8) & 0xff; a.b = (v.w >> 16) & 0xff; a.a = (v.w >> 24) & 0xff;
+    a.rgba = (uint32_t)v.w;
     return a;
 }
-
-// Writes every requested output of one sample from the warp-distributed list.
-__device__ __forceinline__ void emit_sample(const QueryParams &P, uint32_t q, unsigned lane,
-                                            double d, int li)
+__device__ __forceinline__ void store_cand(pt_cand *dst, double d2, int id, const AttrRaw &a)
 {
-    const int k = P.k;
-    bool has = lane < (unsigned)k && li != IDX_NONE;
-    int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
-    if (lane < (unsigned)k) {
-        size_t o = (size_t)q * k + lane;
-        if (P.idx_out) P.idx_out[o] = gid;
-        if (P.d2_out) P.d2_out[o] = has ? d : INFINITY;
-    }
-    bool need_attr = (P.rgba_out || P.normal_out || P.cand_out) && P.attrs;
-    pt_attr at = zero_attr();
-    if (need_attr && has) at = load_attr(P.attrs + li);
-    if (P.cand_out && lane < (unsigned)k) {
-        pt_cand c;
-        c.d2 = has ? d : INFINITY;
-        c.id = gid;
-        c.r = at.r; c.g = at.g; c.b = at.b; c.a = at.a;
-        c.nx = at.nx; c.ny = at.ny; c.nz = at.nz;
-        c.pad_ = 0;
-        P.cand_out[(size_t)q * k + lane] = c;
-    }
-    if (P.rgba_out || P.normal_out)
-        blend_store(lane, has, d, at, P.rgba_out ? P.rgba_out + 4 * (size_t)q : nullptr,
-                    P.normal_out ? P.normal_out + 3 * (size_t)q : nullptr);
+    // pt_cand: d2 | id | rgba | nx ny nz | pad  -> two 16-byte stores
+    int4 lo, hi;
+    lo.x = __double2loint(d2); lo.y = __double2hiint(d2); lo.z = id; lo.w = (int)a.rgba;
+    hi.x = __float_as_int(a.nx); hi.y = __float_as_int(a.ny); hi.z = __float_as_int(a.nz); hi.w = 0;
+    int4 *o = reinterpret_cast<int4 *>(dst);
+    o[0] = lo;
+    o[1] = hi;
 }
 
-// ---- variant 0: warp per sample -----------------------------------------------------------
+// ---- point records ---------------------------------------------------------------------------
 template <typename PT> struct PointLoad;
 template <> struct PointLoad<PointF> {
     static __device__ __forceinline__ void load(const void *base, uint32_t i, double &x, double &y,
@@ -168,22 +116,297 @@ template <> struct PointLoad<PointD> {
         const double2 *p = reinterpret_cast<const double2 *>(base) + 2 * (size_t)i;
         double2 a = __ldg(p), b = __ldg(p + 1);
         x = a.x; y = a.y; z = b.x;
-        idx = (int)(__double_as_longlong(b.y) & 0xffffffffll);
+        idx = __double2loint(b.y);
     }
 };
+
+__device__ __forceinline__ Box load_box(const Box *p)
+{
+    const int4 *bp = reinterpret_cast<const int4 *>(p);
+    int4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+    Box b;
+    b.lox = __int_as_float(b0.x); b.loy = __int_as_float(b0.y);
+    b.loz = __int_as_float(b0.z); b.hix = __int_as_float(b0.w);
+    b.hiy = __int_as_float(b1.x); b.hiz = __int_as_float(b1.y);
+    b.pad0 = 0.f; b.pad1 = 0.f;
+    return b;
+}
+
+// ==============================================================================================
+// Variant 1: thread per sample
+// ==============================================================================================
+constexpr int T_THREADS = 128;
+constexpr int T_LOG = 3;            // 8-wide traversal: pyramid levels 0,3,6,...
+constexpr int T_WIDE = 1 << T_LOG;
+constexpr int PQ_CAP = 160;
+
+// bounded max-heap column in shared memory: element j of this thread at [j * T_THREADS]
+__device__ __forceinline__ void heap_sift_down(double *hd, int *hi, int n, double cd, int ci)
+{
+    int pos = 0;
+    for (;;) {
+        int c = 2 * pos + 1;
+        if (c >= n) break;
+        double xd = hd[c * T_THREADS];
+        int xi = hi[c * T_THREADS];
+        if (c + 1 < n) {
+            double yd = hd[(c + 1) * T_THREADS];
+            int yi = hi[(c + 1) * T_THREADS];
+            if (key_less(xd, xi, yd, yi)) { xd = yd; xi = yi; ++c; }
+        }
+        if (!key_less(cd, ci, xd, xi)) break;
+        hd[pos * T_THREADS] = xd;
+        hi[pos * T_THREADS] = xi;
+        pos = c;
+    }
+    hd[pos * T_THREADS] = cd;
+    hi[pos * T_THREADS] = ci;
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(T_THREADS)
+knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
+{
+    extern __shared__ __align__(16) unsigned char t_smem[];
+    const int k = P.k;
+    double *hd = reinterpret_cast<double *>(t_smem) + threadIdx.x;
+    int *hi = reinterpret_cast<int *>(t_smem + sizeof(double) * k * T_THREADS) + threadIdx.x;
+
+    const uint32_t q = blockIdx.x * T_THREADS + threadIdx.x;
+    bool done = q >= P.m;
+    bool overflow = false;
+
+    double qx = 0, qy = 0, qz = 0, r2 = 0;
+    if (!done) {
+        qx = __ldg(P.queries + 3 * (size_t)q);
+        qy = __ldg(P.queries + 3 * (size_t)q + 1);
+        qz = __ldg(P.queries + 3 * (size_t)q + 2);
+        r2 = P.r2_per_query ? __ldg(P.r2_per_query + q) : P.r2;
+    }
+    const float qdn[3] = {__double2float_rd(qx), __double2float_rd(qy), __double2float_rd(qz)};
+    const float qup[3] = {__double2float_ru(qx), __double2float_ru(qy), __double2float_ru(qz)};
+    for (int j = 0; j < k; ++j) { hd[j * T_THREADS] = INFINITY; hi[j * T_THREADS] = IDX_NONE; }
+    double root_d = INFINITY;     // heap root = current k-th candidate (acceptance threshold)
+    int root_i = IDX_NONE;
+    float bound = __double2float_ru(r2);
+
+    // best-first queue: binary min-heap on the fp32 box bound (bit pattern is monotone, lb >= 0)
+    uint32_t pq_key[PQ_CAP];
+    uint32_t pq_node[PQ_CAP];   // (level / 3) << 28 | node id
+    int pq_n = 0;
+
+    auto pq_push = [&](uint32_t key, uint32_t node) {
+        int i = pq_n++;
+        while (i > 0) {
+            int p = (i - 1) >> 1;
+            uint32_t pk = pq_key[p];
+            if (pk <= key) break;
+            pq_key[i] = pk; pq_node[i] = pq_node[p];
+            i = p;
+        }
+        pq_key[i] = key; pq_node[i] = node;
+    };
+    auto pq_pop = [&](uint32_t &key, uint32_t &node) {
+        key = pq_key[0]; node = pq_node[0];
+        int n = --pq_n;
+        if (n == 0) return;
+        uint32_t lk = pq_key[n], ln = pq_node[n];
+        int i = 0;
+        for (;;) {
+            int c = 2 * i + 1;
+            if (c >= n) break;
+            uint32_t ck = pq_key[c];
+            if (c + 1 < n) { uint32_t ck2 = pq_key[c + 1]; if (ck2 < ck) { ck = ck2; ++c; } }
+            if (ck >= lk) break;
+            pq_key[i] = ck; pq_node[i] = pq_node[c];
+            i = c;
+        }
+        pq_key[i] = lk; pq_node[i] = ln;
+    };
+    // test the (up to 8) children of node `id` at t-level `tl` (children live at t-level tl-1)
+    auto expand = [&](int tl, uint32_t id) {
+        const int pl = (tl - 1) * T_LOG;
+        const uint32_t cnt = P.pyr.count[pl];
+        const Box *boxes = P.pyr.level[pl];
+        const uint32_t first = id * T_WIDE;
+#pragma unroll
+        for (int c = 0; c < T_WIDE; ++c) {
+            uint32_t cid = first + c;
+            if (cid < cnt) {
+                Box b = load_box(boxes + cid);
+                float lb = box_lower_bound(qdn, qup, b);
+                if (lb <= bound) {
+                    if (pq_n == PQ_CAP) { overflow = true; }
+                    else pq_push(__float_as_uint(lb), ((uint32_t)(tl - 1) << 28) | cid);
+                }
+            }
+        }
+    };
+
+    if (!done && P.t_levels > 0) expand(P.t_levels, 0);
+
+    for (;;) {
+        int leaf = -1;
+        if (!done) {
+            while (pq_n > 0 && !overflow) {
+                uint32_t key, node;
+                pq_pop(key, node);
+                if (__uint_as_float(key) > bound) { pq_n = 0; break; }   // everything left is farther
+                int tl = (int)(node >> 28);
+                uint32_t id = node & 0x0fffffffu;
+                if (tl == 0) { leaf = (int)id; break; }
+                expand(tl, id);
+            }
+            if (leaf < 0 || overflow) { done = true; leaf = -1; }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (leaf >= 0) {
+            const uint32_t base = (uint32_t)leaf * LEAF;
+            const uint32_t lim = min((uint32_t)LEAF, P.n - base);
+#pragma unroll 4
+            for (uint32_t p = 0; p < LEAF; ++p) {
+                double px, py, pz;
+                int pidx;
+                PointLoad<PT>::load(P.pts, base + p, px, py, pz, pidx);
+                double d = dist2_exact(qx, qy, qz, px, py, pz);
+                if (p < lim && d <= r2 && key_less(d, pidx, root_d, root_i)) {
+                    heap_sift_down(hd, hi, k, d, pidx);
+                    root_d = hd[0];
+                    root_i = hi[0];
+                }
+            }
+            bound = __double2float_ru(fmin(root_d, r2));
+        }
+    }
+
+    if (q >= P.m) return;
+    if (overflow) {
+        uint32_t slot = atomicAdd(ovf_count, 1u);
+        ovf_list[slot] = q;
+        return;
+    }
+
+    // heap-sort the column in place -> ascending (d2, index); empty slots (IDX_NONE) sort last
+    for (int n = k - 1; n > 0; --n) {
+        double ld = hd[n * T_THREADS];
+        int li = hi[n * T_THREADS];
+        hd[n * T_THREADS] = hd[0];
+        hi[n * T_THREADS] = hi[0];
+        heap_sift_down(hd, hi, n, ld, li);
+    }
+
+    const bool want_blend = P.rgba_out || P.normal_out;
+    const bool need_attr = (want_blend || P.cand_out) && P.attrs;
+    const size_t o = (size_t)q * k;
+    int cnt = 0;
+    int mode = hd[0] == 0.0 ? 1 : 0;
+    BlendAcc acc;
+    acc.reset();
+    for (int j = 0; j < k; ++j) {
+        double d = hd[j * T_THREADS];
+        int li = hi[j * T_THREADS];
+        bool has = li != IDX_NONE;
+        int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
+        if (P.idx_out) P.idx_out[o + j] = gid;
+        if (P.d2_out) P.d2_out[o + j] = has ? d : INFINITY;
+        AttrRaw at{0.f, 0.f, 0.f, 0u};
+        if (has && need_attr) at = load_attr(P.attrs + li);
+        if (P.cand_out) store_cand(P.cand_out + o + j, has ? d : INFINITY, gid, at);
+        if (has) {
+            ++cnt;
+            if (want_blend) acc.add(blend_weight(mode, d, j), at.rgba, at.nx, at.ny, at.nz);
+        }
+    }
+    if (want_blend) {
+        uint8_t *ro = P.rgba_out ? P.rgba_out + 4 * (size_t)q : nullptr;
+        float *no = P.normal_out ? P.normal_out + 3 * (size_t)q : nullptr;
+        if (cnt == 0) { store_empty_blend(ro, no); return; }
+        if (!acc.weight_ok()) {   // overflowed weights: nearest neighbour only
+            acc.reset();
+            AttrRaw at = load_attr(P.attrs + hi[0]);
+            acc.add(1.0, at.rgba, at.nx, at.ny, at.nz);
+        }
+        acc.store(ro, no);
+    }
+}
+
+// ==============================================================================================
+// Variant 0: warp per sample (also the overflow fallback and the K5 merge building block)
+// ==============================================================================================
+struct WarpList {
+    double d;     // lane j holds the j-th best (ascending); +inf when empty
+    int    i;     // local point index; IDX_NONE when empty
+    double kd;    // replicated: current k-th entry (the acceptance threshold)
+    int    ki;
+};
+
+__device__ __forceinline__ double shfl_f64(double v, int src)
+{
+    return __shfl_sync(0xffffffffu, v, src);
+}
+
+// Offer one candidate per lane (pass = lane has a candidate that beats the k-th entry).
+// `tag` rides along with the entry (merge kernel: where the candidate came from).
+__device__ __forceinline__ void warp_list_offer(WarpList &L, int &tag_list, int k, unsigned lane,
+                                                bool pass, double d, int idx, int tag)
+{
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    while (m) {
+        int c = __ffs(m) - 1;
+        m &= m - 1;
+        double cd = shfl_f64(d, c);
+        int ci = __shfl_sync(0xffffffffu, idx, c);
+        int ct = __shfl_sync(0xffffffffu, tag, c);
+        if (!key_less(cd, ci, L.kd, L.ki)) continue;  // threshold moved since the ballot
+        unsigned before = __ballot_sync(0xffffffffu, key_less(L.d, L.i, cd, ci));
+        unsigned pos = __popc(before);
+        double ud = __shfl_up_sync(0xffffffffu, L.d, 1);
+        int ui = __shfl_up_sync(0xffffffffu, L.i, 1);
+        int ut = __shfl_up_sync(0xffffffffu, tag_list, 1);
+        if (lane > pos) { L.d = ud; L.i = ui; tag_list = ut; }
+        else if (lane == pos) { L.d = cd; L.i = ci; tag_list = ct; }
+        L.kd = shfl_f64(L.d, k - 1);
+        L.ki = __shfl_sync(0xffffffffu, L.i, k - 1);
+    }
+}
+
+// Sequential (neighbour-order) blend of a lane-distributed list; every lane runs the same sums.
+__device__ __forceinline__ void warp_blend_store(unsigned lane, int k, bool has, double d2,
+                                                 const AttrRaw &at, uint8_t *rgba_out,
+                                                 float *normal_out)
+{
+    unsigned any = __ballot_sync(0xffffffffu, has);
+    if (any == 0) {
+        if (lane == 0) store_empty_blend(rgba_out, normal_out);
+        return;
+    }
+    const int cnt = __popc(any);   // valid entries are a prefix of the lanes
+    int mode = shfl_f64(d2, 0) == 0.0 ? 1 : 0;
+    BlendAcc acc;
+    for (int pass = 0; pass < 2; ++pass) {
+        acc.reset();
+        for (int j = 0; j < cnt; ++j) {
+            double dj = shfl_f64(d2, j);
+            uint32_t cj = __shfl_sync(0xffffffffu, at.rgba, j);
+            float nx = __shfl_sync(0xffffffffu, at.nx, j);
+            float ny = __shfl_sync(0xffffffffu, at.ny, j);
+            float nz = __shfl_sync(0xffffffffu, at.nz, j);
+            acc.add(blend_weight(mode, dj, j), cj, nx, ny, nz);
+        }
+        if (acc.weight_ok()) break;
+        mode = 2;
+    }
+    (void)k;
+    if (lane == 0) acc.store(rgba_out, normal_out);
+}
 
 constexpr int WARPS_PER_BLOCK = 8;
 
 template <typename PT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) knn_warp_kernel(const QueryParams P)
+__device__ __forceinline__ void warp_query(const QueryParams &P, uint32_t q, unsigned lane,
+                                           float (*s_lb)[32])
 {
-    __shared__ float s_lb[WARPS_PER_BLOCK][MAX_W_LEVELS][32];
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned wib = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * WARPS_PER_BLOCK + wib;
-    if (q >= P.m) return;
     const int k = P.k;
-
     const double qx = __ldg(P.queries + 3 * (size_t)q);
     const double qy = __ldg(P.queries + 3 * (size_t)q + 1);
     const double qz = __ldg(P.queries + 3 * (size_t)q + 2);
@@ -193,6 +416,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) knn_warp_kernel(const Qu
 
     WarpList L;
     L.d = INFINITY; L.i = IDX_NONE; L.kd = INFINITY; L.ki = IDX_NONE;
+    int tag = 0;
     float bound = __double2float_ru(r2);   // prune a box iff its lower bound > bound
 
     // per-level traversal state: lane l keeps level l's group id and pending-children mask
@@ -204,19 +428,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) knn_warp_kernel(const Qu
         const uint32_t node = group * 32 + lane;
         float lb = INFINITY;
         bool valid = node < P.pyr.count[pl];
-        if (valid) {
-            const int4 *bp = reinterpret_cast<const int4 *>(P.pyr.level[pl] + node);
-            int4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-            Box b;
-            b.lox = __int_as_float(b0.x); b.loy = __int_as_float(b0.y);
-            b.loz = __int_as_float(b0.z); b.hix = __int_as_float(b0.w);
-            b.hiy = __int_as_float(b1.x); b.hiz = __int_as_float(b1.y);
-            lb = box_lower_bound(qdn, qup, b);
-        }
-        s_lb[wib][level][lane] = lb;
+        if (valid) lb = box_lower_bound(qdn, qup, load_box(P.pyr.level[pl] + node));
+        s_lb[level][lane] = lb;
         unsigned mask = __ballot_sync(0xffffffffu, valid && lb <= bound);
         if (lane == (unsigned)level) { st_group = group; st_mask = mask; }
-        __syncwarp();
     };
 
     if (lvl >= 0) enter(lvl, 0);
@@ -224,7 +439,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) knn_warp_kernel(const Qu
         unsigned mask = __shfl_sync(0xffffffffu, st_mask, lvl);
         if (mask == 0) { ++lvl; continue; }
         // nearest pending child first
-        float lb = s_lb[wib][lvl][lane];
+        float lb = s_lb[lvl][lane];
         unsigned bits = ((mask >> lane) & 1u) ? __float_as_uint(lb) : 0xffffffffu;
         unsigned mn = __reduce_min_sync(0xffffffffu, bits);
         if (__uint_as_float(mn) > bound) {  // nearest pending child is already too far
@@ -247,10 +462,49 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) knn_warp_kernel(const Qu
         PointLoad<PT>::load(P.pts, i, px, py, pz, pidx);
         double d = dist2_exact(qx, qy, qz, px, py, pz);
         bool pass = i < P.n && d <= r2 && key_less(d, pidx, L.kd, L.ki);
-        warp_list_offer(L, k, lane, pass, d, pidx);
+        warp_list_offer(L, tag, k, lane, pass, d, pidx, 0);
         bound = __double2float_ru(fmin(L.kd, r2));
     }
-    emit_sample(P, q, lane, L.d, L.i);
+
+    // outputs
+    bool has = lane < (unsigned)k && L.i != IDX_NONE;
+    int gid = has ? (P.ids ? __ldg(P.ids + L.i) : L.i) : -1;
+    bool need_attr = (P.rgba_out || P.normal_out || P.cand_out) && P.attrs;
+    AttrRaw at{0.f, 0.f, 0.f, 0u};
+    if (need_attr && has) at = load_attr(P.attrs + L.i);
+    if (lane < (unsigned)k) {
+        size_t o = (size_t)q * k + lane;
+        if (P.idx_out) P.idx_out[o] = gid;
+        if (P.d2_out) P.d2_out[o] = has ? L.d : INFINITY;
+        if (P.cand_out) store_cand(P.cand_out + o, has ? L.d : INFINITY, gid, at);
+    }
+    if (P.rgba_out || P.normal_out)
+        warp_blend_store(lane, k, has, L.d, at, P.rgba_out ? P.rgba_out + 4 * (size_t)q : nullptr,
+                         P.normal_out ? P.normal_out + 3 * (size_t)q : nullptr);
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) knn_warp_kernel(const QueryParams P)
+{
+    __shared__ float s_lb[WARPS_PER_BLOCK][MAX_W_LEVELS][32];
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned wib = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * WARPS_PER_BLOCK + wib;
+    if (q >= P.m) return;
+    warp_query<PT>(P, q, lane, s_lb[wib]);
+}
+
+// Re-runs the samples listed by the thread kernel (queue overflow), grid-stride over the list.
+template <typename PT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+knn_warp_list_kernel(const QueryParams P, const uint32_t *count, const uint32_t *list)
+{
+    __shared__ float s_lb[WARPS_PER_BLOCK][MAX_W_LEVELS][32];
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned wib = threadIdx.x >> 5;
+    const uint32_t n = min(*count, P.m);
+    for (uint32_t w = blockIdx.x * WARPS_PER_BLOCK + wib; w < n; w += gridDim.x * WARPS_PER_BLOCK)
+        warp_query<PT>(P, list[w], lane, s_lb[wib]);
 }
 
 __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
@@ -260,16 +514,44 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
     if (i < total) {
         if (P.idx_out) P.idx_out[i] = -1;
         if (P.d2_out) P.d2_out[i] = INFINITY;
-        if (P.cand_out) {
-            pt_cand c{};
-            c.d2 = INFINITY; c.id = -1;
-            P.cand_out[i] = c;
-        }
+        if (P.cand_out) store_cand(P.cand_out + i, INFINITY, -1, AttrRaw{0.f, 0.f, 0.f, 0u});
     }
-    if (i < P.m) {
-        if (P.rgba_out) *reinterpret_cast<uchar4 *>(P.rgba_out + 4 * i) = make_uchar4(0, 0, 0, 0);
-        if (P.normal_out) { P.normal_out[3 * i] = P.normal_out[3 * i + 1] = P.normal_out[3 * i + 2] = 0.f; }
+    if (i < P.m) store_empty_blend(P.rgba_out ? P.rgba_out + 4 * i : nullptr,
+                                   P.normal_out ? P.normal_out + 3 * i : nullptr);
+}
+
+template <typename PT>
+static int launch_thread_variant(pt_index *ix, const QueryParams &qp, cudaStream_t s)
+{
+    // overflow list lives in the index (grown on demand); count is reset on the stream
+    size_t need = sizeof(uint32_t) * ((size_t)qp.m + 4);
+    if (need > ix->ws_ovf_bytes) {
+        if (ix->ws_ovf) cudaFree(ix->ws_ovf);
+        ix->ws_ovf = nullptr;
+        ix->ws_ovf_bytes = 0;
+        PT_CUDA(cudaMalloc(&ix->ws_ovf, need));
+        ix->ws_ovf_bytes = need;
     }
+    uint32_t *count = (uint32_t *)ix->ws_ovf;
+    uint32_t *list = count + 4;
+    PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
+    size_t smem = (size_t)qp.k * T_THREADS * (sizeof(double) + sizeof(int));
+    static bool attr_set[2] = {false, false};
+    const int which = sizeof(PT) == 32;
+    if (!attr_set[which]) {
+        PT_CUDA(cudaFuncSetAttribute(knn_thread_kernel<PT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     PT_MAX_K * T_THREADS * 12));
+        attr_set[which] = true;
+    }
+    unsigned blocks = (qp.m + T_THREADS - 1) / T_THREADS;
+    knn_thread_kernel<PT><<<blocks, T_THREADS, smem, s>>>(qp, count, list);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    knn_warp_list_kernel<PT><<<148, WARPS_PER_BLOCK * 32, 0, s>>>(qp, count, list);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
 }
 
 int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s)
@@ -283,14 +565,18 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s)
         PT_CUDA(cudaGetLastError());
         return PT_OK;
     }
-    unsigned blocks = (qp.m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    if (ix->coord_f64)
-        knn_warp_kernel<PointD><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(qp);
-    else
-        knn_warp_kernel<PointF><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(qp);
-    count_launch();
-    PT_CUDA(cudaGetLastError());
-    return PT_OK;
+    if (opt_knn_variant() == 0) {
+        unsigned blocks = (qp.m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        if (ix->coord_f64)
+            knn_warp_kernel<PointD><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(qp);
+        else
+            knn_warp_kernel<PointF><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(qp);
+        count_launch();
+        PT_CUDA(cudaGetLastError());
+        return PT_OK;
+    }
+    return ix->coord_f64 ? launch_thread_variant<PointD>(ix, qp, s)
+                         : launch_thread_variant<PointF>(ix, qp, s);
 }
 
 // ---- K5: merge per-slab candidate lists (multi-GPU exchange epilogue) -------------------------
@@ -314,41 +600,24 @@ merge_kernel(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *idx_
             if (id < 0) { id = IDX_NONE; d = INFINITY; }
         }
         bool pass = id != IDX_NONE && key_less(d, id, L.kd, L.ki);
-        // same insertion as warp_list_offer, carrying the source slot along
-        unsigned mk = __ballot_sync(0xffffffffu, pass);
-        while (mk) {
-            int cl = __ffs(mk) - 1;
-            mk &= mk - 1;
-            double cd = shfl_f64(d, cl);
-            int ci = __shfl_sync(0xffffffffu, id, cl);
-            if (!key_less(cd, ci, L.kd, L.ki)) continue;
-            unsigned before = __ballot_sync(0xffffffffu, key_less(L.d, L.i, cd, ci));
-            unsigned pos = __popc(before);
-            double ud = __shfl_up_sync(0xffffffffu, L.d, 1);
-            int ui = __shfl_up_sync(0xffffffffu, L.i, 1);
-            int us = __shfl_up_sync(0xffffffffu, src, 1);
-            if (lane > pos) { L.d = ud; L.i = ui; src = us; }
-            else if (lane == pos) { L.d = cd; L.i = ci; src = l * 32 + cl; }
-            L.kd = shfl_f64(L.d, k - 1);
-            L.ki = __shfl_sync(0xffffffffu, L.i, k - 1);
-        }
+        warp_list_offer(L, src, k, lane, pass, d, id, l * 32 + (int)lane);
     }
     bool has = lane < (unsigned)k && L.i != IDX_NONE;
-    pt_cand mine{};
-    mine.d2 = INFINITY; mine.id = -1;
-    if (has) mine = lists[((size_t)(src >> 5) * m + q) * k + (src & 31)];
+    AttrRaw at{0.f, 0.f, 0.f, 0u};
+    if (has) {
+        const pt_cand *c = lists + ((size_t)(src >> 5) * m + q) * k + (src & 31);
+        at.nx = c->nx; at.ny = c->ny; at.nz = c->nz;
+        at.rgba = (uint32_t)c->r | ((uint32_t)c->g << 8) | ((uint32_t)c->b << 16) | ((uint32_t)c->a << 24);
+    }
     if (lane < (unsigned)k) {
         size_t o = (size_t)q * k + lane;
-        if (idx_out) idx_out[o] = has ? mine.id : -1;
-        if (d2_out) d2_out[o] = has ? mine.d2 : INFINITY;
-        if (cand_out) cand_out[o] = mine;
+        if (idx_out) idx_out[o] = has ? L.i : -1;
+        if (d2_out) d2_out[o] = has ? L.d : INFINITY;
+        if (cand_out) store_cand(cand_out + o, has ? L.d : INFINITY, has ? L.i : -1, at);
     }
-    if (rgba_out || normal_out) {
-        pt_attr at = zero_attr();
-        if (has) { at.nx = mine.nx; at.ny = mine.ny; at.nz = mine.nz; at.r = mine.r; at.g = mine.g; at.b = mine.b; at.a = mine.a; }
-        blend_store(lane, has, L.d, at, rgba_out ? rgba_out + 4 * (size_t)q : nullptr,
-                    normal_out ? normal_out + 3 * (size_t)q : nullptr);
-    }
+    if (rgba_out || normal_out)
+        warp_blend_store(lane, k, has, L.d, at, rgba_out ? rgba_out + 4 * (size_t)q : nullptr,
+                         normal_out ? normal_out + 3 * (size_t)q : nullptr);
 }
 
 int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *idx_out,

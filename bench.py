@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--grid", type=int, default=0, help="override sample grid side per GPU")
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--variant", type=int, default=-1, help="knn kernel variant (tuning)")
+    ap.add_argument("--order", type=int, default=-1, help="0 Morton, 1 Hilbert (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-window", type=float, default=0.25,
                     help="side fraction of the domain used for the bounded CPU sample")
@@ -181,6 +182,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.variant >= 0:
         pkg.set_option("knn_variant", args.variant)
+    if args.order >= 0:
+        pkg.set_option("order", args.order)
 
     w, n, gu, gv, k = resolve_workload(args, pkg)
     L = pkg.synth.L_DOMAIN
@@ -263,7 +266,8 @@ def main():
         "config": {"workload": w.name, "points_per_gpu": n, "samples_per_gpu": m, "k": k,
                    "radius": w.radius, "coord_storage": "f32x4" if info.coord_mode == 1 else "f64",
                    "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": f"slab x{world}", "knn_variant": pkg.get_option("knn_variant")},
+                   "parallelism": f"slab x{world}", "knn_variant": pkg.get_option("knn_variant"),
+                   "order": pkg.get_option("order")},
         "e2e": {"value": world * m / e2e_s, "unit": UNIT, "h2d_bytes_per_step": m * 80,
                 "d2h_bytes_per_step": m * (4 * k + 4 + 12), "ms_per_step": e2e_s * 1e3,
                 "h2d_ms": info2.last_h2d_ms, "kernel_ms": info2.last_query_ms,

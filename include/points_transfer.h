@@ -109,7 +109,7 @@ int pt_transfer(pt_index *index, const void *queries, size_t m, int k,
 
 /* Device-buffer API: same operations with inputs/outputs already resident in
  * HBM on the index's device (bench `value`, multi-GPU slabs).  `stream` is a
- * cudaStream_t passed as void* (NULL = the index's own stream); these calls
+ * cudaStream_t passed as void* (NULL = the CUDA default stream); these calls
  * are asynchronous with respect to the host unless stated. -------------- */
 
 /* 16-byte point attribute record kept in original point order. */

@@ -156,22 +156,25 @@ int pto_knn_bruteforce(const pto_point *pts, int64_t n, const pto_point *queries
     return 0;
 }
 
-/* ---- blend (frozen definition; the reference has none) ---- */
-
-#define PTO_SLOTS 32
-
-static double tree_sum(double *v)
-{
-    for (int s = 1; s < PTO_SLOTS; s <<= 1)
-        for (int j = 0; j < PTO_SLOTS; j += 2 * s) v[j] = v[j] + v[j + s];
-    return v[0];
-}
+/* ---- blend (frozen definition; the reference has none) ----
+ *
+ * For one sample with neighbours j = 0..cnt-1 in ascending (d2, index) order:
+ *   weights  w_j = 1/d2_j;  if d2_0 == 0 (exact hit): w_j = (d2_j == 0) ? 1 : 0;
+ *            if the weight sum overflows (not finite): w_0 = 1, others 0.
+ *   sums     W = sum w_j, C_c = sum w_j*colour_jc, N_a = sum w_j*(double)(float)normal_ja,
+ *            every sum accumulated sequentially in neighbour order, fp64, no FMA.
+ *   colour   trunc(C_c / W) clamped to 0..255 (truncation as src/pointsTransfer.cpp:100-102),
+ *            alpha 255 (:103); input colours are clamped to 0..255 first.
+ *   normal   N / sqrt((Nx*Nx + Ny*Ny) + Nz*Nz) rounded to fp32; zero if the length is 0.
+ *   cnt == 0 rgba = 0,0,0,0 and normal = 0,0,0.
+ */
+#define PTO_MAX_K 32
 
 int pto_blend(const pto_point *pts, int64_t n, int64_t m, int k,
               const int32_t *idx, const double *d2, uint8_t *rgba_out,
               float *normal_out)
 {
-    if (k <= 0 || k > PTO_SLOTS) return 1;
+    if (k <= 0 || k > PTO_MAX_K) return 1;
     int bad_index = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad_index)
     for (int64_t q = 0; q < m; ++q) {
@@ -186,40 +189,29 @@ int pto_blend(const pto_point *pts, int64_t n, int64_t m, int k,
             nrm[0] = nrm[1] = nrm[2] = 0.0f;
             continue;
         }
-        double w[PTO_SLOTS];
         /* 0: 1/d2, 1: exact hits only (d2 == 0), 2: nearest only (weights overflowed) */
         int mode = (qd[0] == 0.0) ? 1 : 0;
+        double s[7];
         for (int pass = 0; pass < 2; ++pass) {
-            for (int j = 0; j < PTO_SLOTS; ++j) {
-                if (j >= cnt) w[j] = 0.0;
-                else if (mode == 0) w[j] = 1.0 / qd[j];
-                else if (mode == 1) w[j] = (qd[j] == 0.0) ? 1.0 : 0.0;
-                else w[j] = (j == 0) ? 1.0 : 0.0;
-            }
-            double t[PTO_SLOTS];
-            memcpy(t, w, sizeof t);
-            double W = tree_sum(t);
-            if (W > 0.0 && W < INFINITY) break;
-            mode = 2; /* overflowed weights: fall back to nearest neighbour */
-        }
-        double acc[7][PTO_SLOTS];
-        for (int j = 0; j < PTO_SLOTS; ++j) {
-            if (j < cnt) {
+            for (int a = 0; a < 7; ++a) s[a] = 0.0;
+            for (int j = 0; j < cnt; ++j) {
+                double w;
+                if (mode == 0) w = 1.0 / qd[j];
+                else if (mode == 1) w = (qd[j] == 0.0) ? 1.0 : 0.0;
+                else w = (j == 0) ? 1.0 : 0.0;
                 if (qi[j] >= n) bad_index = 1;
                 const pto_point *p = &pts[qi[j] >= n ? 0 : qi[j]];
-                acc[0][j] = w[j];
+                s[0] = s[0] + w;
                 for (int c = 0; c < 3; ++c) {
                     int col = p->color[c];
                     col = col < 0 ? 0 : (col > 255 ? 255 : col);
-                    acc[1 + c][j] = w[j] * (double)col;
-                    acc[4 + c][j] = w[j] * (double)(float)p->normal[c];
+                    s[1 + c] = s[1 + c] + w * (double)col;
+                    s[4 + c] = s[4 + c] + w * (double)(float)p->normal[c];
                 }
-            } else {
-                for (int a = 0; a < 7; ++a) acc[a][j] = 0.0;
             }
+            if (s[0] > 0.0 && s[0] < INFINITY) break;
+            mode = 2;
         }
-        double s[7];
-        for (int a = 0; a < 7; ++a) s[a] = tree_sum(acc[a]);
         for (int c = 0; c < 3; ++c) {
             double v = s[1 + c] / s[0];
             int iv = (int)v; /* truncation, src/pointsTransfer.cpp:100-102 */

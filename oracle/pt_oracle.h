@@ -65,9 +65,9 @@ int pto_knn_bruteforce(const pto_point *pts, int64_t n, const pto_point *queries
                        double *d2_out, int nthreads);
 
 /* Frozen blend definition (DESIGN.md "blend"): inverse-squared-distance
- * weights, pairwise (butterfly) fp64 summation over 32 slots, colour
- * truncated like src/pointsTransfer.cpp:100-102, alpha 255 like :103,
- * normal normalised and rounded to fp32.  rgba_out[m*4], normal_out[m*3]. */
+ * weights, sequential fp64 summation in neighbour order, colour truncated
+ * like src/pointsTransfer.cpp:100-102, alpha 255 like :103, normal
+ * normalised and rounded to fp32.  rgba_out[m*4], normal_out[m*3]. */
 int pto_blend(const pto_point *pts, int64_t n, int64_t m, int k,
               const int32_t *idx, const double *d2, uint8_t *rgba_out,
               float *normal_out);

@@ -30,8 +30,22 @@ def _check_blend(got_rgba, got_nrm, ref_rgba, ref_nrm):
     assert np.allclose(got_nrm, ref_nrm, rtol=NORMAL_RTOL, atol=1e-7)
 
 
+@pytest.fixture(autouse=True)
+def _default_options(pkg):
+    yield
+    pkg.set_option("knn_variant", 1)
+    pkg.set_option("order", 1)
+
+
+# (knn_variant, order): thread kernel + Hilbert (default), warp kernel, Morton order
+MODES = [(1, 1), (0, 1), (1, 0)]
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: f"variant{m[0]}-order{m[1]}")
 @pytest.mark.parametrize("name", GOLDEN)
-def test_golden_fixtures(name, pkg, golden_dir, torch_cuda):
+def test_golden_fixtures(name, mode, pkg, golden_dir, torch_cuda):
+    pkg.set_option("knn_variant", mode[0])
+    pkg.set_option("order", mode[1])
     z = np.load(os.path.join(golden_dir, name + ".npz"))
     P = pkg.make_points(z["xyz"], normal=z["normal"], color=z["color"])
     Q = pkg.make_points(z["queries"])
@@ -70,8 +84,10 @@ def test_f64_storage_forced_and_f32_rejected(pkg, pto, torch_cuda):
         assert np.array_equal(idx, ref_idx) and np.array_equal(d2, ref_d2)
 
 
+@pytest.mark.parametrize("variant", [1, 0])
 @pytest.mark.parametrize("k", [1, 8, 16, 20, 32])
-def test_surface_cloud_vs_kdtree_oracle(k, pkg, pto, torch_cuda):
+def test_surface_cloud_vs_kdtree_oracle(k, variant, pkg, pto, torch_cuda):
+    pkg.set_option("knn_variant", variant)
     # config-1 shaped, sized so the oracle finishes in seconds
     P = pkg.synth.cloud_host(300_000, seed=100 + k, side=80.0)
     V = pkg.synth.samples_host(70, side=80.0)
@@ -180,6 +196,27 @@ def test_slab_merge_equals_single_index(n_slabs, k, pkg, pto, torch_cuda):
     _check_blend(rgba.cpu().numpy(), nrm.cpu().numpy(), ref_rgba, ref_nrm)
     for t in trees:
         t.close()
+
+
+def test_queue_overflow_falls_back_exactly(pkg, pto, torch_cuda):
+    """Thousands of exact duplicates make every box bound 0, so the per-thread best-first
+    queue overflows; those samples are re-run by the warp kernel and must stay index-exact
+    (ties -> lowest index)."""
+    rng = np.random.default_rng(77)
+    dup = np.tile(np.array([[0.5, 0.25, 0.125]]), (30_000, 1))
+    rest = rng.random((10_000, 3)).astype(np.float32).astype(np.float64)
+    xyz = np.concatenate([dup, rest])[rng.permutation(40_000)]
+    P = pkg.make_points(xyz, normal=rng.standard_normal((40_000, 3)).astype(np.float32),
+                        color=rng.integers(0, 256, (40_000, 3)))
+    Q = pkg.make_points(np.concatenate([np.array([[0.5, 0.25, 0.125], [0.5, 0.25, 0.2]]),
+                                        rng.random((200, 3))]))
+    for k in (8, 32):
+        ref_idx, ref_d2 = pto.knn_bruteforce(P, Q, k)
+        ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+        with pkg.Tree(P) as tree:
+            out = tree.transfer(Q, k, want_idx=True, want_d2=True)
+        assert np.array_equal(out["idx"], ref_idx) and np.array_equal(out["d2"], ref_d2)
+        _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
 
 
 def test_edge_cases(pkg, torch_cuda):
