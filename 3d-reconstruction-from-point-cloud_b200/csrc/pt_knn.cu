@@ -520,10 +520,15 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
                                    P.normal_out ? P.normal_out + 3 * i : nullptr);
 }
 
+}  // namespace pt
+#include "pt_knn_octet.cuh"
+namespace pt {
+
+// Octet (variant 1) / thread (variant 2) kernel, then the warp kernel over the samples whose
+// private queue overflowed.  The overflow list lives in the index (grown on demand).
 template <typename PT>
-static int launch_thread_variant(pt_index *ix, const QueryParams &qp, cudaStream_t s)
+static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s)
 {
-    // overflow list lives in the index (grown on demand); count is reset on the stream
     size_t need = sizeof(uint32_t) * ((size_t)qp.m + 4);
     if (need > ix->ws_ovf_bytes) {
         if (ix->ws_ovf) cudaFree(ix->ws_ovf);
@@ -535,19 +540,23 @@ static int launch_thread_variant(pt_index *ix, const QueryParams &qp, cudaStream
     uint32_t *count = (uint32_t *)ix->ws_ovf;
     uint32_t *list = count + 4;
     PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
-    size_t smem = (size_t)qp.k * T_THREADS * (sizeof(double) + sizeof(int));
-    static bool attr_set[2] = {false, false};
-    const int which = sizeof(PT) == 32;
-    if (!attr_set[which]) {
-        PT_CUDA(cudaFuncSetAttribute(knn_thread_kernel<PT>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     PT_MAX_K * T_THREADS * 12));
-        attr_set[which] = true;
+    if (variant == 2) {
+        size_t smem = (size_t)qp.k * T_THREADS * (sizeof(double) + sizeof(int));
+        static bool attr_set[2] = {false, false};
+        const int which = sizeof(PT) == 32;
+        if (!attr_set[which]) {
+            PT_CUDA(cudaFuncSetAttribute(knn_thread_kernel<PT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         PT_MAX_K * T_THREADS * 12));
+            attr_set[which] = true;
+        }
+        unsigned blocks = (qp.m + T_THREADS - 1) / T_THREADS;
+        knn_thread_kernel<PT><<<blocks, T_THREADS, smem, s>>>(qp, count, list);
+        count_launch();
+        PT_CUDA(cudaGetLastError());
+    } else {
+        PT_TRY(launch_octet<PT>(qp, count, list, s));
     }
-    unsigned blocks = (qp.m + T_THREADS - 1) / T_THREADS;
-    knn_thread_kernel<PT><<<blocks, T_THREADS, smem, s>>>(qp, count, list);
-    count_launch();
-    PT_CUDA(cudaGetLastError());
     knn_warp_list_kernel<PT><<<148, WARPS_PER_BLOCK * 32, 0, s>>>(qp, count, list);
     count_launch();
     PT_CUDA(cudaGetLastError());
@@ -575,8 +584,9 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s)
         PT_CUDA(cudaGetLastError());
         return PT_OK;
     }
-    return ix->coord_f64 ? launch_thread_variant<PointD>(ix, qp, s)
-                         : launch_thread_variant<PointF>(ix, qp, s);
+    const int variant = opt_knn_variant();
+    return ix->coord_f64 ? launch_with_fallback<PointD>(ix, qp, variant, s)
+                         : launch_with_fallback<PointF>(ix, qp, variant, s);
 }
 
 // ---- K5: merge per-slab candidate lists (multi-GPU exchange epilogue) -------------------------

@@ -37,8 +37,8 @@ def _default_options(pkg):
     pkg.set_option("order", 1)
 
 
-# (knn_variant, order): thread kernel + Hilbert (default), warp kernel, Morton order
-MODES = [(1, 1), (0, 1), (1, 0)]
+# (knn_variant, order): octet kernel + Hilbert (default), warp kernel, thread kernel, Morton order
+MODES = [(1, 1), (0, 1), (2, 1), (1, 0)]
 
 
 @pytest.mark.parametrize("mode", MODES, ids=lambda m: f"variant{m[0]}-order{m[1]}")
@@ -84,7 +84,7 @@ def test_f64_storage_forced_and_f32_rejected(pkg, pto, torch_cuda):
         assert np.array_equal(idx, ref_idx) and np.array_equal(d2, ref_d2)
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [1, 0, 2])
 @pytest.mark.parametrize("k", [1, 8, 16, 20, 32])
 def test_surface_cloud_vs_kdtree_oracle(k, variant, pkg, pto, torch_cuda):
     pkg.set_option("knn_variant", variant)
