@@ -2,14 +2,13 @@
 // `K_neighbor_search search(tree, q, K)` loop, /root/reference src/pointsTransfer.cpp:470-479,
 // metric src/Distance.h:6-11, pruning bound src/Distance.h:27-57).
 //
-// Variant 1 ("thread", default): one thread per sample.  Best-first traversal of the 8-wide
-// levels of the box pyramid with a private priority queue (local memory) ordered by the
-// conservative fp32 box bound; leaves are scanned with the exact fp64 metric into a private
-// bounded max-heap (shared memory, one column per thread).  Samples whose queue overflows are
-// re-run by the warp kernel.
-// Variant 0 ("warp"): one warp per sample, 32-wide levels, nearest-child-first DFS, running
-// top-k as a sorted list distributed one entry per lane.  Slower (instruction bound on the
-// serial list insertions) but has no per-sample state limits: it is the overflow fallback.
+// Three kernels share the helpers in this file:
+//   variant 2 ("thread", pt_knn_thread.cuh): one thread per sample, state in shared-memory columns;
+//   variant 1 ("octet",  pt_knn_octet.cuh) : eight lanes per sample, coalesced 8-wide box tests;
+//   variant 0 ("warp",   below)            : one warp per sample, 32-wide levels, nearest-child-
+//     first DFS, top-k as a sorted list distributed one entry per lane.  Slowest (instruction
+//     bound on the serial list insertions) but has no per-sample state limits: it re-runs the
+//     samples whose private queue overflowed in the other two (exact fallback).
 #include "pt_index.cuh"
 
 namespace pt {
@@ -130,204 +129,6 @@ __device__ __forceinline__ Box load_box(const Box *p)
     b.hiy = __int_as_float(b1.x); b.hiz = __int_as_float(b1.y);
     b.pad0 = 0.f; b.pad1 = 0.f;
     return b;
-}
-
-// ==============================================================================================
-// Variant 1: thread per sample
-// ==============================================================================================
-constexpr int T_THREADS = 128;
-constexpr int T_LOG = 3;            // 8-wide traversal: pyramid levels 0,3,6,...
-constexpr int T_WIDE = 1 << T_LOG;
-constexpr int PQ_CAP = 160;
-
-// bounded max-heap column in shared memory: element j of this thread at [j * T_THREADS]
-__device__ __forceinline__ void heap_sift_down(double *hd, int *hi, int n, double cd, int ci)
-{
-    int pos = 0;
-    for (;;) {
-        int c = 2 * pos + 1;
-        if (c >= n) break;
-        double xd = hd[c * T_THREADS];
-        int xi = hi[c * T_THREADS];
-        if (c + 1 < n) {
-            double yd = hd[(c + 1) * T_THREADS];
-            int yi = hi[(c + 1) * T_THREADS];
-            if (key_less(xd, xi, yd, yi)) { xd = yd; xi = yi; ++c; }
-        }
-        if (!key_less(cd, ci, xd, xi)) break;
-        hd[pos * T_THREADS] = xd;
-        hi[pos * T_THREADS] = xi;
-        pos = c;
-    }
-    hd[pos * T_THREADS] = cd;
-    hi[pos * T_THREADS] = ci;
-}
-
-template <typename PT>
-__global__ void __launch_bounds__(T_THREADS)
-knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
-{
-    extern __shared__ __align__(16) unsigned char t_smem[];
-    const int k = P.k;
-    double *hd = reinterpret_cast<double *>(t_smem) + threadIdx.x;
-    int *hi = reinterpret_cast<int *>(t_smem + sizeof(double) * k * T_THREADS) + threadIdx.x;
-
-    const uint32_t q = blockIdx.x * T_THREADS + threadIdx.x;
-    bool done = q >= P.m;
-    bool overflow = false;
-
-    double qx = 0, qy = 0, qz = 0, r2 = 0;
-    if (!done) {
-        qx = __ldg(P.queries + 3 * (size_t)q);
-        qy = __ldg(P.queries + 3 * (size_t)q + 1);
-        qz = __ldg(P.queries + 3 * (size_t)q + 2);
-        r2 = P.r2_per_query ? __ldg(P.r2_per_query + q) : P.r2;
-    }
-    const float qdn[3] = {__double2float_rd(qx), __double2float_rd(qy), __double2float_rd(qz)};
-    const float qup[3] = {__double2float_ru(qx), __double2float_ru(qy), __double2float_ru(qz)};
-    for (int j = 0; j < k; ++j) { hd[j * T_THREADS] = INFINITY; hi[j * T_THREADS] = IDX_NONE; }
-    double root_d = INFINITY;     // heap root = current k-th candidate (acceptance threshold)
-    int root_i = IDX_NONE;
-    float bound = __double2float_ru(r2);
-
-    // best-first queue: binary min-heap on the fp32 box bound (bit pattern is monotone, lb >= 0)
-    uint32_t pq_key[PQ_CAP];
-    uint32_t pq_node[PQ_CAP];   // (level / 3) << 28 | node id
-    int pq_n = 0;
-
-    auto pq_push = [&](uint32_t key, uint32_t node) {
-        int i = pq_n++;
-        while (i > 0) {
-            int p = (i - 1) >> 1;
-            uint32_t pk = pq_key[p];
-            if (pk <= key) break;
-            pq_key[i] = pk; pq_node[i] = pq_node[p];
-            i = p;
-        }
-        pq_key[i] = key; pq_node[i] = node;
-    };
-    auto pq_pop = [&](uint32_t &key, uint32_t &node) {
-        key = pq_key[0]; node = pq_node[0];
-        int n = --pq_n;
-        if (n == 0) return;
-        uint32_t lk = pq_key[n], ln = pq_node[n];
-        int i = 0;
-        for (;;) {
-            int c = 2 * i + 1;
-            if (c >= n) break;
-            uint32_t ck = pq_key[c];
-            if (c + 1 < n) { uint32_t ck2 = pq_key[c + 1]; if (ck2 < ck) { ck = ck2; ++c; } }
-            if (ck >= lk) break;
-            pq_key[i] = ck; pq_node[i] = pq_node[c];
-            i = c;
-        }
-        pq_key[i] = lk; pq_node[i] = ln;
-    };
-    // test the (up to 8) children of node `id` at t-level `tl` (children live at t-level tl-1)
-    auto expand = [&](int tl, uint32_t id) {
-        const int pl = (tl - 1) * T_LOG;
-        const uint32_t cnt = P.pyr.count[pl];
-        const Box *boxes = P.pyr.level[pl];
-        const uint32_t first = id * T_WIDE;
-#pragma unroll
-        for (int c = 0; c < T_WIDE; ++c) {
-            uint32_t cid = first + c;
-            if (cid < cnt) {
-                Box b = load_box(boxes + cid);
-                float lb = box_lower_bound(qdn, qup, b);
-                if (lb <= bound) {
-                    if (pq_n == PQ_CAP) { overflow = true; }
-                    else pq_push(__float_as_uint(lb), ((uint32_t)(tl - 1) << 28) | cid);
-                }
-            }
-        }
-    };
-
-    if (!done && P.t_levels > 0) expand(P.t_levels, 0);
-
-    for (;;) {
-        int leaf = -1;
-        if (!done) {
-            while (pq_n > 0 && !overflow) {
-                uint32_t key, node;
-                pq_pop(key, node);
-                if (__uint_as_float(key) > bound) { pq_n = 0; break; }   // everything left is farther
-                int tl = (int)(node >> 28);
-                uint32_t id = node & 0x0fffffffu;
-                if (tl == 0) { leaf = (int)id; break; }
-                expand(tl, id);
-            }
-            if (leaf < 0 || overflow) { done = true; leaf = -1; }
-        }
-        if (__all_sync(0xffffffffu, done)) break;
-        if (leaf >= 0) {
-            const uint32_t base = (uint32_t)leaf * LEAF;
-            const uint32_t lim = min((uint32_t)LEAF, P.n - base);
-#pragma unroll 4
-            for (uint32_t p = 0; p < LEAF; ++p) {
-                double px, py, pz;
-                int pidx;
-                PointLoad<PT>::load(P.pts, base + p, px, py, pz, pidx);
-                double d = dist2_exact(qx, qy, qz, px, py, pz);
-                if (p < lim && d <= r2 && key_less(d, pidx, root_d, root_i)) {
-                    heap_sift_down(hd, hi, k, d, pidx);
-                    root_d = hd[0];
-                    root_i = hi[0];
-                }
-            }
-            bound = __double2float_ru(fmin(root_d, r2));
-        }
-    }
-
-    if (q >= P.m) return;
-    if (overflow) {
-        uint32_t slot = atomicAdd(ovf_count, 1u);
-        ovf_list[slot] = q;
-        return;
-    }
-
-    // heap-sort the column in place -> ascending (d2, index); empty slots (IDX_NONE) sort last
-    for (int n = k - 1; n > 0; --n) {
-        double ld = hd[n * T_THREADS];
-        int li = hi[n * T_THREADS];
-        hd[n * T_THREADS] = hd[0];
-        hi[n * T_THREADS] = hi[0];
-        heap_sift_down(hd, hi, n, ld, li);
-    }
-
-    const bool want_blend = P.rgba_out || P.normal_out;
-    const bool need_attr = (want_blend || P.cand_out) && P.attrs;
-    const size_t o = (size_t)q * k;
-    int cnt = 0;
-    int mode = hd[0] == 0.0 ? 1 : 0;
-    BlendAcc acc;
-    acc.reset();
-    for (int j = 0; j < k; ++j) {
-        double d = hd[j * T_THREADS];
-        int li = hi[j * T_THREADS];
-        bool has = li != IDX_NONE;
-        int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
-        if (P.idx_out) P.idx_out[o + j] = gid;
-        if (P.d2_out) P.d2_out[o + j] = has ? d : INFINITY;
-        AttrRaw at{0.f, 0.f, 0.f, 0u};
-        if (has && need_attr) at = load_attr(P.attrs + li);
-        if (P.cand_out) store_cand(P.cand_out + o + j, has ? d : INFINITY, gid, at);
-        if (has) {
-            ++cnt;
-            if (want_blend) acc.add(blend_weight(mode, d, j), at.rgba, at.nx, at.ny, at.nz);
-        }
-    }
-    if (want_blend) {
-        uint8_t *ro = P.rgba_out ? P.rgba_out + 4 * (size_t)q : nullptr;
-        float *no = P.normal_out ? P.normal_out + 3 * (size_t)q : nullptr;
-        if (cnt == 0) { store_empty_blend(ro, no); return; }
-        if (!acc.weight_ok()) {   // overflowed weights: nearest neighbour only
-            acc.reset();
-            AttrRaw at = load_attr(P.attrs + hi[0]);
-            acc.add(1.0, at.rgba, at.nx, at.ny, at.nz);
-        }
-        acc.store(ro, no);
-    }
 }
 
 // ==============================================================================================
@@ -522,6 +323,7 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 
 }  // namespace pt
 #include "pt_knn_octet.cuh"
+#include "pt_knn_thread.cuh"
 namespace pt {
 
 // Octet (variant 1) / thread (variant 2) kernel, then the warp kernel over the samples whose
@@ -541,23 +343,11 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
     uint32_t *list = count + 4;
     PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
     if (variant == 2) {
-        size_t smem = (size_t)qp.k * T_THREADS * (sizeof(double) + sizeof(int));
-        static bool attr_set[2] = {false, false};
-        const int which = sizeof(PT) == 32;
-        if (!attr_set[which]) {
-            PT_CUDA(cudaFuncSetAttribute(knn_thread_kernel<PT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         PT_MAX_K * T_THREADS * 12));
-            attr_set[which] = true;
-        }
-        unsigned blocks = (qp.m + T_THREADS - 1) / T_THREADS;
-        knn_thread_kernel<PT><<<blocks, T_THREADS, smem, s>>>(qp, count, list);
-        count_launch();
-        PT_CUDA(cudaGetLastError());
+        PT_TRY(launch_thread<PT>(qp, count, list, s));
     } else {
         PT_TRY(launch_octet<PT>(qp, count, list, s));
     }
-    knn_warp_list_kernel<PT><<<148, WARPS_PER_BLOCK * 32, 0, s>>>(qp, count, list);
+    knn_warp_list_kernel<PT><<<148 * 4, WARPS_PER_BLOCK * 32, 0, s>>>(qp, count, list);
     count_launch();
     PT_CUDA(cudaGetLastError());
     return PT_OK;

@@ -130,7 +130,10 @@ knn_octet_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
             else {
                 if (pass) {
                     int pos = pq_n + __popc(b & ((1u << l8) - 1u));
-                    pk[pos] = __float_as_uint(lb);
+                    // key = bound with its 4 low mantissa bits replaced by the child's level:
+                    // still a valid (slightly smaller) lower bound, and among equal bounds the
+                    // deeper node pops first, so zero-bound ties descend instead of fanning out
+                    pk[pos] = (__float_as_uint(lb) & ~0xfu) | (uint32_t)(tl - 1);
                     pn[pos] = ((uint32_t)(tl - 1) << 28) | cid;
                 }
                 pq_n += np;
@@ -151,7 +154,8 @@ knn_octet_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         best = min(best, shfl_xor_u64(best, 2));
         best = min(best, shfl_xor_u64(best, 4));
         const uint32_t key = (uint32_t)(best >> 32);
-        bool have = !done && !overflow && best != ~0ull && __uint_as_float(key) <= bound;
+        bool have = !done && !overflow && best != ~0ull &&
+                    __uint_as_float(key & ~0xfu) <= bound;   // low 4 bits carry the level
         if (!have) done = true;
         if (__all_sync(FULL, done)) break;
         uint32_t node = 0;
@@ -200,7 +204,33 @@ knn_octet_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
                     L.insert(go, l8, k, xd, xi);
                 }
             }
-            bound = __double2float_ru(fmin(L.kd, r2));
+            const float nb = __double2float_ru(fmin(L.kd, r2));
+            const bool shrink = is_leaf && nb < bound;
+            bound = nb;
+            // The bound only ever decreases, so queue entries above it are dead: compact them
+            // away (keeps the queue short for pop-min and far from its capacity).
+            const int rounds = (__reduce_max_sync(FULL, shrink ? pq_n : 0) + 7) >> 3;
+            int new_n = 0;
+            for (int t = 0; t < rounds; ++t) {
+                const int e = t * 8 + (int)l8;
+                bool live = shrink && e < pq_n;
+                uint32_t kk = 0, nn = 0;
+                if (live) {
+                    kk = pk[e];
+                    nn = pn[e];
+                    live = __uint_as_float(kk & ~0xfu) <= bound;
+                }
+                const unsigned b = (__ballot_sync(FULL, live) >> oshift) & 0xffu;
+                __syncwarp();
+                if (live) {
+                    const int pos = new_n + __popc(b & ((1u << l8) - 1u));
+                    pk[pos] = kk;
+                    pn[pos] = nn;
+                }
+                new_n += __popc(b);
+                __syncwarp();
+            }
+            if (shrink) pq_n = new_n;
         }
     }
 

@@ -1,0 +1,294 @@
+// pt_knn_thread.cuh -- variant 2 ("thread"): one thread per sample, all per-sample state in
+// shared-memory columns (element j of thread t at [j * T_THREADS + t]: conflict-free).
+//
+//   * traversal : best-first over the 8-wide pyramid levels.  The queue holds one entry per
+//                 partially visited node -- (fp32 bound of its nearest unvisited child, node id,
+//                 8-bit mask of unvisited children) -- so it stays tiny; a popped node is
+//                 re-expanded (its 8 child boxes re-tested) to pick the next child.  After an
+//                 expansion the nearest child is followed directly while it is still the best
+//                 candidate ("dive"), which costs no queue traffic.
+//   * leaf scan : 32 points, exact fp64 metric (src/Distance.h:6-11); candidates that beat the
+//                 current k-th are parked in a small pending column and drained into the heap
+//                 in a warp-converged loop, so heap updates do not serialise the scan.
+//   * top-k     : bounded max-heap column keyed (d2, index); heap-sorted at the end.
+// Samples whose queue overflows go to the warp kernel (exact fallback).
+#pragma once
+
+namespace pt {
+
+constexpr int T_THREADS = 128;
+constexpr int T_LOG = 3;
+constexpr int TPQ_CAP = 24;
+constexpr int TPD_CAP = 8;
+
+// sift `(cd, ci)` down from `pos` in the max-heap column of size n
+__device__ __forceinline__ void heap_sift(double *hd, int *hi, int pos, int n, double cd, int ci)
+{
+    for (;;) {
+        int c = 2 * pos + 1;
+        if (c >= n) break;
+        double xd = hd[c * T_THREADS];
+        int xi = hi[c * T_THREADS];
+        if (c + 1 < n) {
+            double yd = hd[(c + 1) * T_THREADS];
+            int yi = hi[(c + 1) * T_THREADS];
+            if (key_less(xd, xi, yd, yi)) { xd = yd; xi = yi; ++c; }
+        }
+        if (!key_less(cd, ci, xd, xi)) break;
+        hd[pos * T_THREADS] = xd;
+        hi[pos * T_THREADS] = xi;
+        pos = c;
+    }
+    hd[pos * T_THREADS] = cd;
+    hi[pos * T_THREADS] = ci;
+}
+
+__device__ __forceinline__ void heapify(double *hd, int *hi, int n)
+{
+    for (int s = n / 2 - 1; s >= 0; --s)
+        heap_sift(hd, hi, s, n, hd[s * T_THREADS], hi[s * T_THREADS]);
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(T_THREADS)
+knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
+{
+    extern __shared__ __align__(16) unsigned char t_smem[];
+    const int k = P.k;
+    const unsigned tid = threadIdx.x;
+    double *hd = reinterpret_cast<double *>(t_smem) + tid;                      // [k]
+    double *pdd = hd + k * T_THREADS;                                             // [TPD_CAP]
+    int *hi = reinterpret_cast<int *>(t_smem + sizeof(double) * (k + TPD_CAP) * T_THREADS) + tid;
+    int *pdi = hi + k * T_THREADS;                                                // [TPD_CAP]
+    uint32_t *pqk = reinterpret_cast<uint32_t *>(pdi + TPD_CAP * T_THREADS);     // [TPQ_CAP]
+    uint32_t *pqw = pqk + TPQ_CAP * T_THREADS;                                    // [TPQ_CAP]
+
+    const uint32_t q = blockIdx.x * T_THREADS + tid;
+    bool done = q >= P.m || P.t_levels == 0;
+    bool overflow = false;
+
+    double qx = 0, qy = 0, qz = 0, r2 = 0;
+    if (q < P.m) {
+        qx = __ldg(P.queries + 3 * (size_t)q);
+        qy = __ldg(P.queries + 3 * (size_t)q + 1);
+        qz = __ldg(P.queries + 3 * (size_t)q + 2);
+        r2 = P.r2_per_query ? __ldg(P.r2_per_query + q) : P.r2;
+    }
+    const float qdn[3] = {__double2float_rd(qx), __double2float_rd(qy), __double2float_rd(qz)};
+    const float qup[3] = {__double2float_ru(qx), __double2float_ru(qy), __double2float_ru(qz)};
+    float bound = __double2float_ru(r2);
+
+    int hn = 0;                 // candidates held; the column is a max-heap once hn == k
+    double root_d = INFINITY;   // heap root (current k-th) -- meaningful once hn == k
+    int root_i = IDX_NONE;
+    int pq_n = 0;
+
+    // queue entry: key = bound bits with the low 4 mantissa bits replaced by the node's t-level
+    // (still a valid, slightly smaller lower bound); word = unvisited-children mask << 23 | id
+    auto pq_push = [&](uint32_t key, uint32_t word) {
+        if (pq_n == TPQ_CAP) { overflow = true; return; }
+        int i = pq_n++;
+        while (i > 0) {
+            int p = (i - 1) >> 1;
+            uint32_t pk = pqk[p * T_THREADS];
+            if (pk <= key) break;
+            pqk[i * T_THREADS] = pk;
+            pqw[i * T_THREADS] = pqw[p * T_THREADS];
+            i = p;
+        }
+        pqk[i * T_THREADS] = key;
+        pqw[i * T_THREADS] = word;
+    };
+    auto pq_pop = [&](uint32_t &key, uint32_t &word) {
+        key = pqk[0];
+        word = pqw[0];
+        const int n = --pq_n;
+        if (n == 0) return;
+        const uint32_t lk = pqk[n * T_THREADS], lw = pqw[n * T_THREADS];
+        int i = 0;
+        for (;;) {
+            int c = 2 * i + 1;
+            if (c >= n) break;
+            uint32_t ck = pqk[c * T_THREADS];
+            if (c + 1 < n) {
+                uint32_t ck2 = pqk[(c + 1) * T_THREADS];
+                if (ck2 < ck) { ck = ck2; ++c; }
+            }
+            if (ck >= lk) break;
+            pqk[i * T_THREADS] = ck;
+            pqw[i * T_THREADS] = pqw[c * T_THREADS];
+            i = c;
+        }
+        pqk[i * T_THREADS] = lk;
+        pqw[i * T_THREADS] = lw;
+    };
+
+    // the node being expanded (not in the queue)
+    bool cur_valid = !done;
+    int cur_tl = P.t_levels;
+    uint32_t cur_id = 0, cur_mask = 0xffu;
+
+    for (;;) {
+        int leaf = -1;
+        while (!done && leaf < 0) {
+            if (!cur_valid) {
+                if (pq_n == 0) { done = true; break; }
+                uint32_t key, word;
+                pq_pop(key, word);
+                if (__uint_as_float(key & ~0xfu) > bound) { done = true; break; }  // rest is farther
+                cur_tl = (int)(key & 0xfu);
+                cur_id = word & 0x7fffffu;
+                cur_mask = word >> 23;
+            }
+            cur_valid = false;
+            // expand: test the unvisited children (t-level cur_tl - 1)
+            const int pl = (cur_tl - 1) * T_LOG;
+            const uint32_t cnt = P.pyr.count[pl];
+            const Box *boxes = P.pyr.level[pl] + (size_t)cur_id * 8;
+            float best = INFINITY, second = INFINITY;
+            int best_c = -1;
+            uint32_t rem = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (((cur_mask >> c) & 1u) && cur_id * 8 + c < cnt) {
+                    const float lb = box_lower_bound(qdn, qup, load_box(boxes + c));
+                    if (lb <= bound) {
+                        rem |= 1u << c;
+                        if (lb < best) { second = best; best = lb; best_c = c; }
+                        else second = fminf(second, lb);
+                    }
+                }
+            }
+            if (best_c < 0) continue;
+            rem &= ~(1u << best_c);
+            if (rem) pq_push((__float_as_uint(second) & ~0xfu) | (uint32_t)cur_tl, (rem << 23) | cur_id);
+            const uint32_t child = cur_id * 8 + (uint32_t)best_c;
+            if (cur_tl == 1) {
+                leaf = (int)child;
+            } else {
+                const bool dive = hn < k || pq_n == 0 ||
+                                  best <= __uint_as_float(pqk[0] & ~0xfu);
+                if (dive) { cur_valid = true; cur_tl -= 1; cur_id = child; cur_mask = 0xffu; }
+                else pq_push((__float_as_uint(best) & ~0xfu) | (uint32_t)(cur_tl - 1),
+                             (0xffu << 23) | child);
+            }
+            if (overflow) { done = true; leaf = -1; }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+
+        // ---- leaf phase: every lane that holds a leaf scans it, 8 points per chunk -------------
+        const uint32_t base = (uint32_t)(leaf < 0 ? 0 : leaf) * LEAF;
+#pragma unroll 1
+        for (int chunk = 0; chunk < LEAF / 8; ++chunk) {
+            int pend = 0;
+            if (leaf >= 0) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const uint32_t pi = base + chunk * 8 + p;
+                    double px, py, pz;
+                    int pidx;
+                    PointLoad<PT>::load(P.pts, pi, px, py, pz, pidx);
+                    const double d = dist2_exact(qx, qy, qz, px, py, pz);
+                    if (pi < P.n && d <= r2 && (hn < k || key_less(d, pidx, root_d, root_i))) {
+                        pdd[pend * T_THREADS] = d;
+                        pdi[pend * T_THREADS] = pidx;
+                        ++pend;
+                    }
+                }
+            }
+            while (__any_sync(0xffffffffu, pend > 0)) {
+                if (pend > 0) {
+                    --pend;
+                    const double d = pdd[pend * T_THREADS];
+                    const int pidx = pdi[pend * T_THREADS];
+                    if (hn < k) {
+                        hd[hn * T_THREADS] = d;
+                        hi[hn * T_THREADS] = pidx;
+                        if (++hn == k) {
+                            heapify(hd, hi, k);
+                            root_d = hd[0];
+                            root_i = hi[0];
+                        }
+                    } else if (key_less(d, pidx, root_d, root_i)) {
+                        heap_sift(hd, hi, 0, k, d, pidx);
+                        root_d = hd[0];
+                        root_i = hi[0];
+                    }
+                }
+            }
+        }
+        if (hn == k) bound = __double2float_ru(fmin(root_d, r2));
+    }
+
+    if (q >= P.m) return;
+    if (overflow) {
+        uint32_t slot = atomicAdd(ovf_count, 1u);
+        ovf_list[slot] = q;
+        return;
+    }
+
+    // heap-sort the hn held candidates in place -> ascending (d2, index)
+    if (hn < k) heapify(hd, hi, hn);
+    for (int n = hn - 1; n > 0; --n) {
+        const double ld = hd[n * T_THREADS];
+        const int li = hi[n * T_THREADS];
+        hd[n * T_THREADS] = hd[0];
+        hi[n * T_THREADS] = hi[0];
+        heap_sift(hd, hi, 0, n, ld, li);
+    }
+
+    const bool want_blend = P.rgba_out || P.normal_out;
+    const bool need_attr = (want_blend || P.cand_out) && P.attrs;
+    const size_t o = (size_t)q * k;
+    const int mode = (hn > 0 && hd[0] == 0.0) ? 1 : 0;
+    BlendAcc acc;
+    acc.reset();
+    for (int j = 0; j < k; ++j) {
+        const bool has = j < hn;
+        const double d = has ? hd[j * T_THREADS] : INFINITY;
+        const int li = has ? hi[j * T_THREADS] : IDX_NONE;
+        const int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
+        if (P.idx_out) P.idx_out[o + j] = gid;
+        if (P.d2_out) P.d2_out[o + j] = d;
+        AttrRaw at{0.f, 0.f, 0.f, 0u};
+        if (has && need_attr) at = load_attr(P.attrs + li);
+        if (P.cand_out) store_cand(P.cand_out + o + j, d, gid, at);
+        if (has && want_blend) acc.add(blend_weight(mode, d, j), at.rgba, at.nx, at.ny, at.nz);
+    }
+    if (want_blend) {
+        uint8_t *ro = P.rgba_out ? P.rgba_out + 4 * (size_t)q : nullptr;
+        float *no = P.normal_out ? P.normal_out + 3 * (size_t)q : nullptr;
+        if (hn == 0) { store_empty_blend(ro, no); return; }
+        if (!acc.weight_ok()) {   // overflowed weights: nearest neighbour only
+            acc.reset();
+            AttrRaw at = load_attr(P.attrs + hi[0]);
+            acc.add(1.0, at.rgba, at.nx, at.ny, at.nz);
+        }
+        acc.store(ro, no);
+    }
+}
+
+static inline size_t thread_kernel_smem(int k)
+{
+    return (size_t)T_THREADS * ((size_t)(k + TPD_CAP) * 12 + (size_t)TPQ_CAP * 8);
+}
+
+template <typename PT>
+static int launch_thread(const QueryParams &qp, uint32_t *count, uint32_t *list, cudaStream_t s)
+{
+    static bool attr_set[2] = {false, false};
+    const int which = sizeof(PT) == 32;
+    if (!attr_set[which]) {
+        PT_CUDA(cudaFuncSetAttribute(knn_thread_kernel<PT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)thread_kernel_smem(PT_MAX_K)));
+        attr_set[which] = true;
+    }
+    unsigned blocks = (qp.m + T_THREADS - 1) / T_THREADS;
+    knn_thread_kernel<PT><<<blocks, T_THREADS, thread_kernel_smem(qp.k), s>>>(qp, count, list);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+}  // namespace pt
