@@ -18,7 +18,13 @@ namespace pt {
 
 constexpr int T_THREADS = 128;
 constexpr int T_LOG = 3;
-constexpr int TPQ_CAP = 24;
+#ifndef PT_TPQ_CAP
+#define PT_TPQ_CAP 24
+#endif
+#ifndef PT_T_BATCH_BOXES
+#define PT_T_BATCH_BOXES 1
+#endif
+constexpr int TPQ_CAP = PT_TPQ_CAP;
 constexpr int TPD_CAP = 8;
 
 // sift `(cd, ci)` down from `pos` in the max-heap column of size n
@@ -86,7 +92,29 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     // queue entry: key = bound bits with the low 4 mantissa bits replaced by the node's t-level
     // (still a valid, slightly smaller lower bound); word = unvisited-children mask << 23 | id
     auto pq_push = [&](uint32_t key, uint32_t word) {
-        if (pq_n == TPQ_CAP) { overflow = true; return; }
+        if (pq_n == TPQ_CAP) {
+            // full: the bound only decreases, so entries above it are dead -- drop them and
+            // rebuild the heap (rare); only a queue full of live entries is an overflow
+            int live = 0;
+            for (int e = 0; e < TPQ_CAP; ++e) {
+                const uint32_t ek = pqk[e * T_THREADS], ew = pqw[e * T_THREADS];
+                if (__uint_as_float(ek & ~0xfu) <= bound) {
+                    int i = live++;
+                    while (i > 0) {
+                        int p = (i - 1) >> 1;
+                        uint32_t pk = pqk[p * T_THREADS];
+                        if (pk <= ek) break;
+                        pqk[i * T_THREADS] = pk;
+                        pqw[i * T_THREADS] = pqw[p * T_THREADS];
+                        i = p;
+                    }
+                    pqk[i * T_THREADS] = ek;
+                    pqw[i * T_THREADS] = ew;
+                }
+            }
+            pq_n = live;
+            if (pq_n == TPQ_CAP) { overflow = true; return; }
+        }
         int i = pq_n++;
         while (i > 0) {
             int p = (i - 1) >> 1;
@@ -144,14 +172,25 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
             // expand: test the unvisited children (t-level cur_tl - 1)
             const int pl = (cur_tl - 1) * T_LOG;
             const uint32_t cnt = P.pyr.count[pl];
-            const Box *boxes = P.pyr.level[pl] + (size_t)cur_id * 8;
+            const Box *boxes = P.pyr.level[pl];
             float best = INFINITY, second = INFINITY;
             int best_c = -1;
             uint32_t rem = 0;
+            // all 8 child boxes are fetched up front (16 independent 16-byte loads in flight);
+            // children past the end of the level are clamped and masked out below
+#if PT_T_BATCH_BOXES
+            Box cb[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cb[c] = load_box(boxes + min(cur_id * 8 + c, cnt - 1));
+#endif
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (((cur_mask >> c) & 1u) && cur_id * 8 + c < cnt) {
-                    const float lb = box_lower_bound(qdn, qup, load_box(boxes + c));
+#if PT_T_BATCH_BOXES
+                    const float lb = box_lower_bound(qdn, qup, cb[c]);
+#else
+                    const float lb = box_lower_bound(qdn, qup, load_box(boxes + cur_id * 8 + c));
+#endif
                     if (lb <= bound) {
                         rem |= 1u << c;
                         if (lb < best) { second = best; best = lb; best_c = c; }
