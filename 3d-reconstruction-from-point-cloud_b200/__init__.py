@@ -11,3 +11,4 @@ from .api import (  # noqa: F401
     status_string, version,
 )
 from . import synth  # noqa: F401
+from . import dist  # noqa: F401,E402

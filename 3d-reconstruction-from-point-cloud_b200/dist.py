@@ -1,0 +1,182 @@
+"""Slab-sharded detail transfer across the GPUs of one box.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink).  Every rank owns one spatial
+slab of the cloud and its own index; every sample is owned by exactly one rank.  A sample is
+answered by its owner; only if the ball of its k-th neighbour reaches another slab's bounding
+box does it take part in the single exchange step:
+
+  1. owner:  local k-NN                          -> candidates + k-th squared distance (bound)
+  2. route:  samples whose ball touches slab r   -> all_to_all (xyz + bound), usually a sliver
+  3. remote: radius-bounded k-NN (d2 <= bound)   -> candidate lists, all_to_all back
+  4. owner:  K5 merge kernel (key (d2, global id)) + blend of the merged list
+
+so the result is bit-identical to a single index over the whole cloud, for any slab count.
+The reference has no distributed path ("NCCL / MPI / Gloo: none"); this is
+new plumbing around the same kernels.
+
+The numerical work is delegated to an *engine* (``CudaSlabEngine`` in production).  The host
+logic here only touches tensors through torch, so it also runs on CPU tensors over ``gloo``,
+which is how the world_size-2 tests exercise it without a GPU.
+"""
+import torch
+import torch.distributed as dist
+
+CAND_BYTES = 32
+
+
+def box_lower_bound2(q, lo, hi):
+    """Squared distance from points q[m,3] to the box [lo, hi] (Distance.h:27-57), fp64, shrunk
+    by a relative 1e-12 so that rounding can never exclude a slab that holds a neighbour."""
+    e = torch.clamp(torch.maximum(lo - q, q - hi), min=0.0)
+    return (e * e).sum(dim=1) * (1.0 - 1e-12)
+
+
+class CudaSlabEngine:
+    """The production engine: this rank's slab index on its GPU (hand-written CUDA kernels)."""
+
+    def __init__(self, tree):
+        from . import api
+        self._api = api
+        self.tree = tree
+        info = tree.info()
+        dev = tree.torch_device
+        self.device = dev
+        self.n_points = int(info.n_points)
+        self.bbox_lo = torch.tensor(list(info.bbox_lo), dtype=torch.float64, device=dev)
+        self.bbox_hi = torch.tensor(list(info.bbox_hi), dtype=torch.float64, device=dev)
+
+    def query(self, q, k, radius=None, radius2_per_query=None, outputs=False, want_d2=False):
+        """-> (cand uint8 [m, k, 32] pt_cand records (d2, global id, attributes), out) where
+        out is None or, with ``outputs``, the fused-blend results of the same launch."""
+        m = q.shape[0]
+        dev = q.device
+        cand = torch.empty((m, k, CAND_BYTES), dtype=torch.uint8, device=dev)
+        out = None
+        if outputs:
+            out = {"idx": torch.empty((m, k), dtype=torch.int32, device=dev),
+                   "rgba": torch.empty((m, 4), dtype=torch.uint8, device=dev),
+                   "normal": torch.empty((m, 3), dtype=torch.float32, device=dev)}
+            if want_d2:
+                out["d2"] = torch.empty((m, k), dtype=torch.float64, device=dev)
+        if m:
+            self.tree.query(q, k, radius=radius, radius2_per_query=radius2_per_query,
+                            cand=cand.view(-1), idx=out["idx"] if out else None,
+                            d2=out.get("d2") if out else None,
+                            rgba=out["rgba"] if out else None,
+                            normal=out["normal"] if out else None)
+        return cand, out
+
+    def merge(self, lists, k, want_d2=False):
+        """lists uint8 [R, m, k, 32] -> dict(idx, rgba, normal[, d2])."""
+        r, m = lists.shape[0], lists.shape[1]
+        dev = lists.device
+        out = {"idx": torch.empty((m, k), dtype=torch.int32, device=dev),
+               "rgba": torch.empty((m, 4), dtype=torch.uint8, device=dev),
+               "normal": torch.empty((m, 3), dtype=torch.float32, device=dev)}
+        if want_d2:
+            out["d2"] = torch.empty((m, k), dtype=torch.float64, device=dev)
+        if m:
+            self._api.merge_device(lists.contiguous().view(-1), r, m, k, idx=out["idx"],
+                                   d2=out.get("d2"), rgba=out["rgba"], normal=out["normal"])
+        return out
+
+
+def cand_d2(cand):
+    """k-th ... view the squared distances of pt_cand records: cand uint8 [..., 32] -> f64 [...]."""
+    return cand[..., :8].contiguous().view(torch.float64).squeeze(-1)
+
+
+def empty_cand(shape, device):
+    """Candidate records meaning "no neighbour": d2 = +inf, id = -1."""
+    c = torch.zeros(tuple(shape) + (CAND_BYTES,), dtype=torch.uint8, device=device)
+    c[..., :8] = torch.tensor([float("inf")], dtype=torch.float64).view(torch.uint8).to(device)
+    c[..., 8:12] = torch.tensor([-1], dtype=torch.int32).view(torch.uint8).to(device)
+    return c
+
+
+class SlabTransfer:
+    """Collective detail transfer: every rank calls ``transfer`` with the samples it owns."""
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dev = engine.device
+        box = torch.stack([engine.bbox_lo, engine.bbox_hi]).to(torch.float64)
+        if engine.n_points == 0:           # an empty slab can never hold a neighbour
+            box[0].fill_(float("inf"))
+            box[1].fill_(float("-inf"))
+        if self.world > 1:
+            boxes = [torch.empty_like(box) for _ in range(self.world)]
+            dist.all_gather(boxes, box, group=group)
+            self.boxes = torch.stack(boxes)          # [R, 2, 3]
+        else:
+            self.boxes = box[None]
+        self.device = dev
+        self.stats = {}
+
+    def _all_to_all(self, send, send_counts, width, dtype):
+        """Variable-size exchange of rows ([n, width] tensors ordered by destination rank)."""
+        dev = self.device
+        sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        recv_counts = rc.tolist()
+        recv = torch.empty((sum(recv_counts), width), dtype=dtype, device=dev)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=recv_counts,
+                               input_split_sizes=list(send_counts), group=self.group)
+        return recv, recv_counts
+
+    def transfer(self, q, k, radius=None, want_d2=False):
+        """q float64 [m,3] on the engine's device (samples owned by this rank).
+        Returns dict(idx int32 [m,k] global ids, rgba uint8 [m,4], normal float32 [m,3][, d2])."""
+        eng, dev, R = self.engine, self.device, self.world
+        m = q.shape[0]
+        r2 = float("inf") if (radius is None or radius < 0) else float(radius) * float(radius)
+        own, out = eng.query(q, k, radius=radius, outputs=True, want_d2=want_d2)   # [m, k, 32]
+        if R == 1:
+            self.stats = {"crossing": 0, "sent": 0, "received": 0}
+            return out
+        # bound = squared distance of the k-th local neighbour (inf while the list is short)
+        bound = torch.clamp(cand_d2(own)[:, k - 1], max=r2) if m else q.new_empty((0,))
+        send_rows, send_counts, send_sel = [], [], []
+        for r in range(R):
+            if r == self.rank or m == 0:
+                sel = torch.empty((0,), dtype=torch.int64, device=dev)
+            else:
+                lb = box_lower_bound2(q, self.boxes[r, 0], self.boxes[r, 1])
+                sel = torch.nonzero(lb <= bound).view(-1)
+            send_sel.append(sel)
+            send_counts.append(int(sel.numel()))
+            send_rows.append(torch.cat([q[sel], bound[sel, None]], dim=1))
+        send = torch.cat(send_rows) if send_rows else q.new_empty((0, 4))
+        recv, recv_counts = self._all_to_all(send, send_counts, 4, torch.float64)
+        # halo search for the other ranks' samples, bounded by their k-th distance
+        rq = recv[:, :3].contiguous()
+        rb = recv[:, 3].contiguous()
+        halo, _ = eng.query(rq, k, radius=None, radius2_per_query=rb)  # [n_recv, k, 32]
+        back, back_counts = self._all_to_all(halo.view(-1, k * CAND_BYTES), recv_counts,
+                                             k * CAND_BYTES, torch.uint8)
+        assert back_counts == send_counts
+        # merge: own list + one list per rank that was asked
+        cross = torch.unique(torch.cat(send_sel)) if sum(send_counts) else \
+            torch.empty((0,), dtype=torch.int64, device=dev)
+        nc = int(cross.numel())
+        if nc:
+            lists = empty_cand((R, nc, k), dev)
+            pos = torch.full((m,), -1, dtype=torch.int64, device=dev)
+            pos[cross] = torch.arange(nc, device=dev)
+            lists[self.rank] = own[cross]
+            off = 0
+            for r in range(R):
+                c = send_counts[r]
+                if c:
+                    lists[r, pos[send_sel[r]]] = back[off:off + c].view(c, k, CAND_BYTES)
+                off += c
+            merged = eng.merge(lists, k, want_d2=want_d2)
+            for name, t in merged.items():
+                out[name][cross] = t
+        self.stats = {"crossing": nc, "sent": int(sum(send_counts)),
+                      "received": int(sum(recv_counts))}
+        return out

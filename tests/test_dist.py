@@ -1,0 +1,165 @@
+"""world_size-2 (and 3) `gloo` tests of the slab-sharding host logic.
+
+The routing / exchange / merge bookkeeping in ``dist.SlabTransfer`` runs on CPU tensors here;
+the numerical engine is a numpy stand-in built on the oracle (test infrastructure), so no GPU
+is needed.  The GPU engine itself is covered by tests/test_gpu_parity.py (slab merge) and
+tests/test_gpu_dist.py.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleEngine:
+    """CPU stand-in for CudaSlabEngine: brute-force k-NN on this rank's slab via the oracle."""
+
+    def __init__(self, pkg, pto, points, ids):
+        self.pkg, self.pto = pkg, pto
+        self.points, self.ids = points, ids.astype(np.int32)
+        self.device = torch.device("cpu")
+        self.n_points = len(points)
+        xyz = points["ver"] if len(points) else np.zeros((1, 3))
+        self.bbox_lo = torch.from_numpy(xyz.min(0).copy())
+        self.bbox_hi = torch.from_numpy(xyz.max(0).copy())
+
+    def _cands(self, idx, d2):
+        m, k = idx.shape
+        c = np.zeros((m, k), dtype=self.pkg.CAND_DTYPE)
+        has = idx >= 0
+        safe = np.where(has, idx, 0)
+        c["d2"] = np.where(has, d2, np.inf)
+        c["id"] = np.where(has, self.ids[safe] if len(self.ids) else 0, -1)
+        if len(self.points):
+            col = np.clip(self.points["color"][safe], 0, 255).astype(np.uint8)
+            c["rgba"][..., :3] = np.where(has[..., None], col, 0)
+            c["rgba"][..., 3] = np.where(has, 255, 0)
+            nrm = self.points["normal"][safe].astype(np.float32)
+            c["nx"], c["ny"], c["nz"] = [np.where(has, nrm[..., a], 0) for a in range(3)]
+        return c
+
+    def query(self, q, k, radius=None, radius2_per_query=None, outputs=False, want_d2=False):
+        qn = q.numpy()
+        m = qn.shape[0]
+        Q = self.pkg.make_points(qn)
+        if m == 0 or self.n_points == 0:
+            idx = np.full((m, k), -1, np.int32)
+            d2 = np.full((m, k), np.inf)
+        else:
+            idx, d2 = self.pto.knn_bruteforce(self.points, Q, k,
+                                              radius=-1.0 if radius is None else radius)
+            if radius2_per_query is not None:     # per-sample squared bound: d2 <= bound
+                keep = d2 <= radius2_per_query.numpy()[:, None]
+                idx = np.where(keep, idx, -1)
+                d2 = np.where(keep, d2, np.inf)
+        cand = torch.from_numpy(self._cands(idx, d2).view(np.uint8).reshape(m, k, 32).copy())
+        out = None
+        if outputs:
+            out = self.merge(cand[None], k, want_d2=want_d2)
+        return cand, out
+
+    def merge(self, lists, k, want_d2=False):
+        r, m = lists.shape[0], lists.shape[1]
+        c = lists.numpy().reshape(r, m, k, 32).view(self.pkg.CAND_DTYPE).reshape(r, m, k)
+        c = np.transpose(c, (1, 0, 2)).reshape(m, r * k)
+        key_id = np.where(c["id"] < 0, np.iinfo(np.int32).max, c["id"])
+        order = np.lexsort((key_id, c["d2"]), axis=1)[:, :k]
+        sel = np.take_along_axis(c, order, axis=1)
+        # blend with the oracle's definition on a scratch cloud made of the selected records
+        flat = sel.reshape(-1)
+        P = self.pkg.make_points(np.zeros((len(flat), 3)),
+                                 normal=np.stack([flat["nx"], flat["ny"], flat["nz"]], 1),
+                                 color=flat["rgba"][:, :3].astype(np.int32))
+        idx_local = np.arange(len(flat), dtype=np.int32).reshape(m, k)
+        idx_local = np.where(sel["id"] >= 0, idx_local, -1)
+        rgba, nrm = self.pto.blend(P, idx_local, np.where(sel["id"] >= 0, sel["d2"], np.inf)) \
+            if m else (np.zeros((0, 4), np.uint8), np.zeros((0, 3), np.float32))
+        out = {"idx": torch.from_numpy(sel["id"].astype(np.int32).copy()),
+               "rgba": torch.from_numpy(rgba), "normal": torch.from_numpy(nrm)}
+        if want_d2:
+            out["d2"] = torch.from_numpy(sel["d2"].copy())
+        return out
+
+
+def _worker(rank, world, port, case, tmpdir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import __graft_entry__ as ge
+        from oracle import pto
+        pkg = ge.package()
+        k, radius = case["k"], case["radius"]
+        P = pkg.synth.cloud_host(case["n"], seed=5, side=40.0)
+        V = pkg.synth.samples_host(case["g"], side=40.0)
+        # slabs at point-count quantiles along x; ids ascending inside each slab
+        order = np.argsort(P["ver"][:, 0], kind="stable")
+        cuts = np.linspace(0, len(P), world + 1).astype(int)
+        mine = np.sort(order[cuts[rank]:cuts[rank + 1]])
+        if case.get("empty_rank") == rank:
+            mine = mine[:0]
+        x_cut = [-np.inf] + [P["ver"][order[c], 0] for c in cuts[1:-1]] + [np.inf]
+        own_q = np.nonzero((V["ver"][:, 0] >= x_cut[rank]) & (V["ver"][:, 0] < x_cut[rank + 1]))[0]
+        eng = OracleEngine(pkg, pto, P[mine], mine)
+        st = pkg.dist.SlabTransfer(eng)
+        out = st.transfer(torch.from_numpy(np.ascontiguousarray(V["ver"][own_q])), k,
+                          radius=radius, want_d2=True)
+        # reference: one index over the points every rank actually holds
+        held = [np.sort(order[cuts[r]:cuts[r + 1]]) for r in range(world)
+                if case.get("empty_rank") != r]
+        held = np.sort(np.concatenate(held))
+        ref_idx, ref_d2 = pto.knn_bruteforce(P[held], V[own_q], k,
+                                             radius=-1.0 if radius is None else radius)
+        ref_rgba, ref_nrm = pto.blend(P[held], ref_idx, ref_d2)
+        ref_gid = np.where(ref_idx >= 0, held[np.maximum(ref_idx, 0)], -1)
+        assert np.array_equal(out["idx"].numpy(), ref_gid), f"rank {rank}: indices"
+        assert np.array_equal(out["d2"].numpy(), ref_d2), f"rank {rank}: d2"
+        assert np.array_equal(out["rgba"].numpy(), ref_rgba), f"rank {rank}: rgba"
+        assert np.allclose(out["normal"].numpy(), ref_nrm, rtol=1e-5, atol=1e-7)
+        stats = torch.tensor([st.stats["crossing"], len(own_q)], dtype=torch.int64)
+        dist.all_reduce(stats)
+        if rank == 0:
+            open(os.path.join(tmpdir, "stats.txt"), "w").write(f"{stats[0].item()} {stats[1].item()}")
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = {
+    "unbounded_k8": dict(n=40_000, g=40, k=8, radius=None),
+    "radius_k16": dict(n=40_000, g=40, k=16, radius=0.5),
+    "tiny_cloud_k32": dict(n=50, g=10, k=32, radius=None),       # every sample crosses
+    "empty_slab": dict(n=20_000, g=30, k=8, radius=None, empty_rank=1),
+}
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_slab_transfer_matches_single_index(case, world, tmp_path):
+    if world == 3 and case not in ("unbounded_k8", "tiny_cloud_k32"):
+        pytest.skip("covered at world_size 2")
+    port = 29500 + (os.getpid() * 7 + hash(case) + world) % 2000
+    mp.spawn(_worker, args=(world, port, CASES[case], str(tmp_path)), nprocs=world, join=True)
+    crossing, total = map(int, open(tmp_path / "stats.txt").read().split())
+    assert total == CASES[case]["g"] ** 2
+    if case == "unbounded_k8":
+        assert 0 < crossing < total // 4      # only a sliver of the samples is exchanged
+    if case == "tiny_cloud_k32":
+        assert crossing == total
+
+
+def test_box_lower_bound_is_conservative(pkg):
+    rng = np.random.default_rng(0)
+    lo = torch.tensor([0.0, 0.0, 0.0], dtype=torch.float64)
+    hi = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    q = torch.from_numpy(rng.normal(0, 3, (1000, 3)))
+    lb = pkg.dist.box_lower_bound2(q, lo, hi)
+    p = torch.from_numpy(rng.random((1000, 3))) * hi          # points inside the box
+    d2 = ((q - p) ** 2).sum(1)
+    assert bool((lb <= d2).all())
