@@ -12,8 +12,8 @@ namespace pt {
 
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_verbose{-1};
-static std::atomic<int> g_knn_variant{1};
-static std::atomic<int> g_order{1};
+static std::atomic<int> g_knn_variant{2};   // 2 thread (default), 1 octet, 0 warp
+static std::atomic<int> g_order{2};   // 0 Morton, 1 Hilbert, 2 Hilbert + kd refinement (default)
 
 bool verbose()
 {

@@ -111,7 +111,7 @@ __device__ __forceinline__ unsigned long long hilbert63(unsigned int x, unsigned
 struct KeyParams {
     double lo[3];
     double inv_cell;   // 2^21 / max extent (0 when the cloud is a single point)
-    int    order;      // 0 = Morton, 1 = Hilbert
+    int    order;      // 0 = Morton, 1 = Hilbert, 2 = Hilbert + in-block kd refinement
 };
 
 template <typename In>
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) morton_kernel(In in, uint32_t n, KeyParam
         t = fmin(fmax(t, 0.0), 2097151.0);
         c[a] = (unsigned int)t;
     }
-    keys[i] = kp.order == 1 ? hilbert63(c[0], c[1], c[2])
+    keys[i] = kp.order >= 1 ? hilbert63(c[0], c[1], c[2])
                             : (spread21(c[0]) | (spread21(c[1]) << 1) | (spread21(c[2]) << 2));
     vals[i] = i;
 }
@@ -154,6 +154,112 @@ __global__ void __launch_bounds__(256) gather_kernel(In in, const uint32_t *perm
     }
     if constexpr (sizeof(Out) == 32) o.pad = 0;
     out[i] = o;
+}
+
+// ---- kd refinement of the curve order (order = 2) ----------------------------------------------
+// A run of consecutive Hilbert keys is a compact blob, but a 32-point run inside it is not a
+// compact cell.  Each CTA takes one aligned block of BLK sorted records (128 KiB of shared
+// memory), and splits it recursively at the count median along the widest axis of the segment
+// (a balanced kd-tree by sorting: bitonic sort of every segment, log2(BLK/32) levels), so every
+// aligned run of 32*2^j records -- i.e. every pyramid node below the block -- becomes a kd cell.
+// In simulation this cuts the leaves a query scans from 5.5 to 3.4 (tools/sim_tree.py).
+__device__ __forceinline__ int ord_f32(float f)
+{
+    int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+
+template <typename Out>
+__device__ __forceinline__ bool kd_after(const Out &a, const Out &b, int axis)
+{
+    const auto ka = axis == 0 ? a.x : (axis == 1 ? a.y : a.z);
+    const auto kb = axis == 0 ? b.x : (axis == 1 ? b.y : b.z);
+    return ka > kb || (ka == kb && a.idx > b.idx);
+}
+
+template <typename Out, int BLK>
+__global__ void __launch_bounds__(1024, 1) kd_refine_kernel(Out *pts, uint32_t n_pad)
+{
+    extern __shared__ __align__(16) unsigned char kd_smem[];
+    Out *s = reinterpret_cast<Out *>(kd_smem);
+    constexpr int MAXSEG = BLK / (2 * LEAF);
+    __shared__ int seg_lo[3][MAXSEG], seg_hi[3][MAXSEG];
+    __shared__ unsigned char seg_axis[MAXSEG];
+    const uint32_t base = blockIdx.x * (uint32_t)BLK;
+    const uint32_t cnt = min((uint32_t)BLK, n_pad - base);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < BLK; i += 1024) {
+        Out p;
+        if ((uint32_t)i < cnt) p = pts[base + i];
+        else {
+            p.x = FLT_MAX; p.y = FLT_MAX; p.z = FLT_MAX; p.idx = IDX_NONE;
+            if constexpr (sizeof(Out) == 32) p.pad = 0;
+        }
+        s[i] = p;
+    }
+    __syncthreads();
+    for (int sz = BLK; sz > LEAF; sz >>= 1) {
+        const int nseg = BLK / sz;
+        const int shift = __ffs(sz) - 1;
+        if (tid < nseg) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { seg_lo[a][tid] = 0x7fffffff; seg_hi[a][tid] = (int)0x80000000; }
+        }
+        __syncthreads();
+        for (int i = tid; i < BLK; i += 1024) {
+            const Out p = s[i];
+            if (p.idx != IDX_NONE) {
+                const int sg = i >> shift;
+                const int ex = ord_f32((float)p.x), ey = ord_f32((float)p.y), ez = ord_f32((float)p.z);
+                atomicMin(&seg_lo[0][sg], ex); atomicMax(&seg_hi[0][sg], ex);
+                atomicMin(&seg_lo[1][sg], ey); atomicMax(&seg_hi[1][sg], ey);
+                atomicMin(&seg_lo[2][sg], ez); atomicMax(&seg_hi[2][sg], ez);
+            }
+        }
+        __syncthreads();
+        if (tid < nseg) {
+            float ext[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                int lo = seg_lo[a][tid], hi = seg_hi[a][tid];
+                float flo = __int_as_float(lo ^ ((lo >> 31) & 0x7fffffff));
+                float fhi = __int_as_float(hi ^ ((hi >> 31) & 0x7fffffff));
+                ext[a] = hi >= lo ? fhi - flo : -1.0f;
+            }
+            int ax = 0;
+            if (ext[1] > ext[ax]) ax = 1;
+            if (ext[2] > ext[ax]) ax = 2;
+            seg_axis[tid] = (unsigned char)ax;
+        }
+        __syncthreads();
+        for (int kk = 2; kk <= sz; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < BLK / 2; t += 1024) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const int ax = seg_axis[i >> shift];
+                    const bool asc = ((i & (sz - 1)) & kk) == 0;
+                    const Out a = s[i], b = s[l];
+                    if (kd_after(a, b, ax) == asc) { s[i] = b; s[l] = a; }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (int i = tid; (uint32_t)i < cnt; i += 1024) pts[base + i] = s[i];
+}
+
+template <typename Out>
+static int kd_refine(Out *pts, uint32_t n_pad, cudaStream_t s)
+{
+    constexpr int BLK = sizeof(Out) == 16 ? 8192 : 4096;
+    const size_t smem = (size_t)BLK * sizeof(Out);
+    PT_CUDA(cudaFuncSetAttribute(kd_refine_kernel<Out, BLK>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kd_refine_kernel<Out, BLK><<<(n_pad + BLK - 1) / BLK, 1024, smem, s>>>(pts, n_pad);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
 }
 
 // ---- leaf boxes: one warp per 32-point leaf ------------------------------------------------
@@ -294,6 +400,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     gather_kernel<In, Out><<<cdiv(n_pad, 256), 256, 0, s>>>(in, vals, n, (uint32_t)n_pad, pts);
     count_launch();
     ix->pts = pts;
+    if (kp.order == 2) PT_TRY(kd_refine<Out>(pts, (uint32_t)n_pad, s));
 
     // box pyramid
     uint64_t total = 0;

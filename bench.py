@@ -193,6 +193,7 @@ def main():
     q = pkg.synth.samples_device(gu, gv, u0=u0, u1=u1, center=w.center, device=dev)
     m = q.shape[0]
     torch.cuda.synchronize()
+    pkg.DeviceTree(pos, attrs).close()          # warm-up build (module load, allocator)
     t0 = time.perf_counter()
     tree = pkg.DeviceTree(pos, attrs)
     build_wall_ms = (time.perf_counter() - t0) * 1e3
