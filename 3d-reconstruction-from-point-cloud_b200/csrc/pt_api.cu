@@ -93,7 +93,7 @@ static void destroy_index(pt_index *ix)
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     cudaFree(ix->pts); cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->boxes);
-    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf);
+    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf); cudaFree(ix->ws_scr);
     for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;

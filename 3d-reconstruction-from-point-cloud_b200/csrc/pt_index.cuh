@@ -26,6 +26,7 @@ struct pt_index {
     void  *ws_q = nullptr;     size_t ws_q_bytes = 0;      // m*3 doubles
     void  *ws_out = nullptr;   size_t ws_out_bytes = 0;    // idx | d2 | rgba | normal
     void  *ws_ovf = nullptr;   size_t ws_ovf_bytes = 0;    // queue-overflow count + sample list
+    void  *ws_scr = nullptr;   size_t ws_scr_bytes = 0;    // persistent kernel: parked candidates
 };
 
 namespace pt {
