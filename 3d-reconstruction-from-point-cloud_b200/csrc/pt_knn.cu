@@ -324,7 +324,6 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 }  // namespace pt
 #include "pt_knn_octet.cuh"
 #include "pt_knn_thread.cuh"
-#include "pt_knn_persist.cuh"
 namespace pt {
 
 // Octet (variant 1) / thread (variant 2) kernel, then the warp kernel over the samples whose
@@ -343,17 +342,7 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
     uint32_t *count = (uint32_t *)ix->ws_ovf;
     uint32_t *list = count + 4;
     PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
-    if (variant == 3) {
-        size_t scr = persist_scratch_bytes(qp.m, qp.k);
-        if (scr > ix->ws_scr_bytes) {
-            if (ix->ws_scr) cudaFree(ix->ws_scr);
-            ix->ws_scr = nullptr;
-            ix->ws_scr_bytes = 0;
-            PT_CUDA(cudaMalloc(&ix->ws_scr, scr + scr / 4));
-            ix->ws_scr_bytes = scr + scr / 4;
-        }
-        PT_TRY(launch_persist<PT>(qp, ix->ws_scr, count, list, s));
-    } else if (variant == 2) {
+    if (variant == 2) {
         PT_TRY(launch_thread<PT>(qp, count, list, s));
     } else {
         PT_TRY(launch_octet<PT>(qp, count, list, s));

@@ -16,7 +16,16 @@
 
 namespace pt {
 
-constexpr int T_THREADS = 128;
+#ifndef PT_T_THREADS
+#define PT_T_THREADS 32      // one warp per block: finest scheduling granularity (sweep: 32 > 64 > 128)
+#endif
+#ifndef PT_T_CHUNK
+#define PT_T_CHUNK 8          // leaf points scanned between two drains (= pending capacity)
+#endif
+#ifndef PT_T_PREFETCH
+#define PT_T_PREFETCH 1       // L2-prefetch the chosen leaf while other lanes still traverse
+#endif
+constexpr int T_THREADS = PT_T_THREADS;
 constexpr int T_LOG = 3;
 #ifndef PT_TPQ_CAP
 #define PT_TPQ_CAP 24
@@ -25,7 +34,7 @@ constexpr int T_LOG = 3;
 #define PT_T_BATCH_BOXES 1
 #endif
 constexpr int TPQ_CAP = PT_TPQ_CAP;
-constexpr int TPD_CAP = 8;
+constexpr int TPD_CAP = PT_T_CHUNK;
 
 // sift `(cd, ci)` down from `pos` in the max-heap column of size n
 __device__ __forceinline__ void heap_sift(double *hd, int *hi, int pos, int n, double cd, int ci)
@@ -204,6 +213,14 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
             const uint32_t child = cur_id * 8 + (uint32_t)best_c;
             if (cur_tl == 1) {
                 leaf = (int)child;
+#if PT_T_PREFETCH
+                {
+                    const char *lp = reinterpret_cast<const char *>(P.pts) + (size_t)child * LEAF * sizeof(PT);
+#pragma unroll
+                    for (int l = 0; l < (int)(LEAF * sizeof(PT) / 128); ++l)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + 128 * l));
+                }
+#endif
             } else {
                 const bool dive = hn < k || pq_n == 0 ||
                                   best <= __uint_as_float(pqk[0] & ~0xfu);
@@ -218,12 +235,12 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         // ---- leaf phase: every lane that holds a leaf scans it, 8 points per chunk -------------
         const uint32_t base = (uint32_t)(leaf < 0 ? 0 : leaf) * LEAF;
 #pragma unroll 1
-        for (int chunk = 0; chunk < LEAF / 8; ++chunk) {
+        for (int chunk = 0; chunk < LEAF / PT_T_CHUNK; ++chunk) {
             int pend = 0;
             if (leaf >= 0) {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const uint32_t pi = base + chunk * 8 + p;
+                for (int p = 0; p < PT_T_CHUNK; ++p) {
+                    const uint32_t pi = base + chunk * PT_T_CHUNK + p;
                     double px, py, pz;
                     int pidx;
                     PointLoad<PT>::load(P.pts, pi, px, py, pz, pidx);
