@@ -93,7 +93,9 @@ static void destroy_index(pt_index *ix)
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     cudaFree(ix->pts); cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->boxes);
-    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf); cudaFree(ix->ws_scr);
+    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf);
+    for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
+    for (auto &e : ix->cev) if (e) cudaEventDestroy(e);
     for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -235,14 +237,11 @@ int pt_index_get_info(const pt_index *ix, pt_index_info *info)
     return PT_OK;
 }
 
-int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, double radius,
-                    const double *radius2_per_query, int32_t *idx_out, double *d2_out,
-                    uint8_t *rgba_out, float *normal_out, pt_cand *cand_out, void *stream)
+static int query_device_slot(pt_index *ix, const double *queries_xyz, size_t m, int k, double radius,
+                             const double *radius2_per_query, int32_t *idx_out, double *d2_out,
+                             uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
+                             cudaStream_t stream, int slot)
 {
-    if (!ix || (!queries_xyz && m) || m > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
-    if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
-    if ((rgba_out || normal_out) && !ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
-    PT_CUDA(cudaSetDevice(ix->device));
     QueryParams qp{};
     fill_params(ix, qp);
     qp.queries = queries_xyz;
@@ -252,7 +251,20 @@ int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, do
     qp.r2 = radius_to_r2(radius);
     qp.idx_out = idx_out; qp.d2_out = d2_out; qp.rgba_out = rgba_out;
     qp.normal_out = normal_out; qp.cand_out = cand_out;
-    return launch_query(ix, qp, (cudaStream_t)stream);
+    return launch_query(ix, qp, stream, slot);
+}
+
+int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, double radius,
+                    const double *radius2_per_query, int32_t *idx_out, double *d2_out,
+                    uint8_t *rgba_out, float *normal_out, pt_cand *cand_out, void *stream)
+{
+    if (!ix || (!queries_xyz && m) || m > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
+    if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
+    if ((rgba_out || normal_out) && !ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
+    PT_CUDA(cudaSetDevice(ix->device));
+    PT_TRY(ensure_overflow_slots(ix, (uint32_t)m, 1));
+    return query_device_slot(ix, queries_xyz, m, k, radius, radius2_per_query, idx_out, d2_out,
+                             rgba_out, normal_out, cand_out, (cudaStream_t)stream, 0);
 }
 
 int pt_merge_device(const pt_cand *lists, int n_lists, size_t m, int k, int32_t *idx_out,
@@ -266,11 +278,15 @@ int pt_merge_device(const pt_cand *lists, int n_lists, size_t m, int k, int32_t 
                         cand_out, (cudaStream_t)stream);
 }
 
+// Host-buffer query.  Large batches are cut into chunks that are pipelined over three streams so
+// the H2D copy of the 80-byte records, the kernels and the D2H copy of the results overlap
+// (pinned caller buffers make the copies truly asynchronous; pageable ones still work).
 static int host_query(pt_index *ix, const void *queries, size_t m, int k, double radius,
                       int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out)
 {
     if (!ix || (!queries && m) || m > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
     if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
+    if ((rgba_out || normal_out) && !ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
     if (m == 0) return PT_OK;
     PT_CUDA(cudaSetDevice(ix->device));
     cudaStream_t s = ix->stream;
@@ -285,26 +301,49 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
     PT_TRY(grow(&ix->ws_out, &ix->ws_out_bytes, total ? total : 16));
     char *o = (char *)ix->ws_out;
 
+    constexpr int NCS = 3;
+    size_t chunk = m;
+    if (m >= 32768) chunk = (((m + 3) / 4) + 31) & ~(size_t)31;
+    const int n_chunks = (int)((m + chunk - 1) / chunk);
+    const int n_streams = n_chunks < NCS ? n_chunks : NCS;
+    for (int i = 0; i < n_streams; ++i) {
+        if (!ix->cs[i]) PT_CUDA(cudaStreamCreateWithFlags(&ix->cs[i], cudaStreamNonBlocking));
+        if (!ix->cev[i]) PT_CUDA(cudaEventCreateWithFlags(&ix->cev[i], cudaEventDisableTiming));
+    }
+    PT_TRY(ensure_overflow_slots(ix, (uint32_t)chunk, n_streams));
+
     PT_CUDA(cudaEventRecord(ix->ev[0], s));
-    PT_CUDA(cudaMemcpyAsync(ix->ws_raw, queries, m * PT_POINT_STRIDE, cudaMemcpyHostToDevice, s));
-    PT_TRY(unpack_queries_aos(ix->ws_raw, m, (double *)ix->ws_q, s));
-    PT_CUDA(cudaEventRecord(ix->ev[1], s));
-    int rc = pt_query_device(ix, (const double *)ix->ws_q, m, k, radius, nullptr,
-                             idx_out ? (int32_t *)(o + off_idx) : nullptr,
-                             d2_out ? (double *)(o + off_d2) : nullptr,
-                             rgba_out ? (uint8_t *)(o + off_rgba) : nullptr,
-                             normal_out ? (float *)(o + off_nrm) : nullptr, nullptr, (void *)s);
-    if (rc != PT_OK) return rc;
-    PT_CUDA(cudaEventRecord(ix->ev[2], s));
-    if (d2_out) PT_CUDA(cudaMemcpyAsync(d2_out, o + off_d2, mk * 8, cudaMemcpyDeviceToHost, s));
-    if (idx_out) PT_CUDA(cudaMemcpyAsync(idx_out, o + off_idx, mk * 4, cudaMemcpyDeviceToHost, s));
-    if (normal_out) PT_CUDA(cudaMemcpyAsync(normal_out, o + off_nrm, m * 12, cudaMemcpyDeviceToHost, s));
-    if (rgba_out) PT_CUDA(cudaMemcpyAsync(rgba_out, o + off_rgba, m * 4, cudaMemcpyDeviceToHost, s));
+    for (int i = 0; i < n_streams; ++i) PT_CUDA(cudaStreamWaitEvent(ix->cs[i], ix->ev[0], 0));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int si = c % NCS;
+        cudaStream_t st = ix->cs[si];
+        const size_t c0 = (size_t)c * chunk;
+        const size_t cm = m - c0 < chunk ? m - c0 : chunk;
+        char *raw = (char *)ix->ws_raw + c0 * PT_POINT_STRIDE;
+        double *qd = (double *)ix->ws_q + 3 * c0;
+        PT_CUDA(cudaMemcpyAsync(raw, (const char *)queries + c0 * PT_POINT_STRIDE,
+                                cm * PT_POINT_STRIDE, cudaMemcpyHostToDevice, st));
+        PT_TRY(unpack_queries_aos(raw, cm, qd, st));
+        PT_TRY(query_device_slot(ix, qd, cm, k, radius, nullptr,
+                                 idx_out ? (int32_t *)(o + off_idx) + c0 * k : nullptr,
+                                 d2_out ? (double *)(o + off_d2) + c0 * k : nullptr,
+                                 rgba_out ? (uint8_t *)(o + off_rgba) + c0 * 4 : nullptr,
+                                 normal_out ? (float *)(o + off_nrm) + c0 * 3 : nullptr, nullptr,
+                                 st, si));
+        if (d2_out) PT_CUDA(cudaMemcpyAsync(d2_out + c0 * k, (double *)(o + off_d2) + c0 * k, cm * k * 8, cudaMemcpyDeviceToHost, st));
+        if (idx_out) PT_CUDA(cudaMemcpyAsync(idx_out + c0 * k, (int32_t *)(o + off_idx) + c0 * k, cm * k * 4, cudaMemcpyDeviceToHost, st));
+        if (normal_out) PT_CUDA(cudaMemcpyAsync(normal_out + c0 * 3, (float *)(o + off_nrm) + c0 * 3, cm * 12, cudaMemcpyDeviceToHost, st));
+        if (rgba_out) PT_CUDA(cudaMemcpyAsync(rgba_out + c0 * 4, (uint8_t *)(o + off_rgba) + c0 * 4, cm * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < n_streams; ++i) {
+        PT_CUDA(cudaEventRecord(ix->cev[i], ix->cs[i]));
+        PT_CUDA(cudaStreamWaitEvent(s, ix->cev[i], 0));
+    }
     PT_CUDA(cudaEventRecord(ix->ev[3], s));
     PT_CUDA(cudaStreamSynchronize(s));
-    cudaEventElapsedTime(&ix->last_h2d_ms, ix->ev[0], ix->ev[1]);
-    cudaEventElapsedTime(&ix->last_query_ms, ix->ev[1], ix->ev[2]);
-    cudaEventElapsedTime(&ix->last_d2h_ms, ix->ev[2], ix->ev[3]);
+    ix->last_h2d_ms = 0.f;          // overlapped with the kernels: only the total is meaningful
+    ix->last_d2h_ms = 0.f;
+    cudaEventElapsedTime(&ix->last_query_ms, ix->ev[0], ix->ev[3]);
     return PT_OK;
 }
 

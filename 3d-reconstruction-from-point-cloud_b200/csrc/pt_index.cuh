@@ -25,8 +25,10 @@ struct pt_index {
     void  *ws_raw = nullptr;   size_t ws_raw_bytes = 0;    // uploaded 80-byte query records
     void  *ws_q = nullptr;     size_t ws_q_bytes = 0;      // m*3 doubles
     void  *ws_out = nullptr;   size_t ws_out_bytes = 0;    // idx | d2 | rgba | normal
-    void  *ws_ovf = nullptr;   size_t ws_ovf_bytes = 0;    // queue-overflow count + sample list
-    void  *ws_scr = nullptr;   size_t ws_scr_bytes = 0;    // persistent kernel: parked candidates
+    void  *ws_ovf = nullptr;   size_t ws_ovf_bytes = 0;    // queue-overflow count + sample list,
+    uint32_t ovf_slot_words = 0;                           //   one slot per concurrent launch
+    cudaStream_t cs[3]{};                                  // chunk streams of the host-buffer API
+    cudaEvent_t  cev[3]{};
 };
 
 namespace pt {
@@ -69,7 +71,8 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
                       bool *representable);
 int unpack_queries_aos(const void *raw80_dev, size_t m, double *xyz_dev, cudaStream_t s);
 
-int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s);
+int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots);
+int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot = 0);
 int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *idx_out,
                  double *d2_out, uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
                  cudaStream_t s);

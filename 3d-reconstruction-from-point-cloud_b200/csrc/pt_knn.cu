@@ -329,17 +329,13 @@ namespace pt {
 // Octet (variant 1) / thread (variant 2) kernel, then the warp kernel over the samples whose
 // private queue overflowed.  The overflow list lives in the index (grown on demand).
 template <typename PT>
-static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s)
+static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s,
+                                int slot)
 {
-    size_t need = sizeof(uint32_t) * ((size_t)qp.m + 4);
-    if (need > ix->ws_ovf_bytes) {
-        if (ix->ws_ovf) cudaFree(ix->ws_ovf);
-        ix->ws_ovf = nullptr;
-        ix->ws_ovf_bytes = 0;
-        PT_CUDA(cudaMalloc(&ix->ws_ovf, need));
-        ix->ws_ovf_bytes = need;
-    }
-    uint32_t *count = (uint32_t *)ix->ws_ovf;
+    if ((size_t)(slot + 1) * ix->ovf_slot_words * sizeof(uint32_t) > ix->ws_ovf_bytes ||
+        qp.m + 4 > ix->ovf_slot_words)
+        return PT_ERR_INVALID_ARG;   // ensure_overflow_slots() was not called for this launch
+    uint32_t *count = (uint32_t *)ix->ws_ovf + (size_t)slot * ix->ovf_slot_words;
     uint32_t *list = count + 4;
     PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
     if (variant == 2) {
@@ -353,7 +349,25 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
     return PT_OK;
 }
 
-int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s)
+// Sizes the overflow workspace for `slots` concurrent launches of up to m_per_slot samples.
+// Reallocates (device-synchronising) only when it has to grow.
+int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots)
+{
+    uint32_t words = m_per_slot + 4;
+    if (words < ix->ovf_slot_words) words = ix->ovf_slot_words;
+    size_t need = sizeof(uint32_t) * (size_t)words * slots;
+    if (need > ix->ws_ovf_bytes) {
+        if (ix->ws_ovf) cudaFree(ix->ws_ovf);
+        ix->ws_ovf = nullptr;
+        ix->ws_ovf_bytes = 0;
+        PT_CUDA(cudaMalloc(&ix->ws_ovf, need));
+        ix->ws_ovf_bytes = need;
+    }
+    ix->ovf_slot_words = words;
+    return PT_OK;
+}
+
+int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
 {
     if (qp.m == 0) return PT_OK;
     if (qp.k < 1 || qp.k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
@@ -375,8 +389,8 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s)
         return PT_OK;
     }
     const int variant = opt_knn_variant();
-    return ix->coord_f64 ? launch_with_fallback<PointD>(ix, qp, variant, s)
-                         : launch_with_fallback<PointF>(ix, qp, variant, s);
+    return ix->coord_f64 ? launch_with_fallback<PointD>(ix, qp, variant, s, slot)
+                         : launch_with_fallback<PointF>(ix, qp, variant, s, slot);
 }
 
 // ---- K5: merge per-slab candidate lists (multi-GPU exchange epilogue) -------------------------

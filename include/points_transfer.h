@@ -79,8 +79,9 @@ typedef struct pt_index_info {
     double   bbox_lo[3], bbox_hi[3];
     uint64_t device_bytes;   /* resident after the build */
     float    build_ms;       /* device time of the last build (CUDA events) */
-    float    last_query_ms;  /* device time of the last pt_knn/pt_transfer kernels */
-    float    last_h2d_ms, last_d2h_ms;
+    float    last_query_ms;  /* device time of the last pt_knn/pt_transfer call: the chunked
+                                H2D copy, kernels and D2H copy are pipelined over 3 streams */
+    float    last_h2d_ms, last_d2h_ms; /* 0: overlapped, not separately measurable */
 } pt_index_info;
 
 /* Library / device probing (no compute). */
