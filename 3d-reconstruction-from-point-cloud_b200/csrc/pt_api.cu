@@ -278,6 +278,35 @@ int pt_merge_device(const pt_cand *lists, int n_lists, size_t m, int k, int32_t 
                         cand_out, (cudaStream_t)stream);
 }
 
+int pt_halo_route_device(const double *queries_xyz, const pt_cand *own_cand, size_t m, int k,
+                         double radius, const double *boxes, int n_ranks, int self, uint32_t cap,
+                         double *send, int32_t *sel, uint32_t *counts, uint32_t *overflow_flag,
+                         void *stream)
+{
+    if ((m && (!queries_xyz || !own_cand)) || !boxes || !send || !sel || !counts || !overflow_flag ||
+        m > 0xfffffff0ull || self < 0 || self >= n_ranks)
+        return PT_ERR_INVALID_ARG;
+    return launch_halo_route(queries_xyz, own_cand, (uint32_t)m, k, radius_to_r2(radius), boxes,
+                             n_ranks, self, cap, send, sel, counts, overflow_flag,
+                             (cudaStream_t)stream);
+}
+
+int pt_halo_prepare_device(const double *recv, int n_ranks, uint32_t cap, double *queries_out,
+                           double *radius2_out, void *stream)
+{
+    if (!recv || !queries_out || !radius2_out || n_ranks < 1) return PT_ERR_INVALID_ARG;
+    return launch_halo_prepare(recv, n_ranks, cap, queries_out, radius2_out, (cudaStream_t)stream);
+}
+
+int pt_halo_merge_device(pt_cand *own_cand, const pt_cand *back, const int32_t *sel,
+                         const uint32_t *count, uint32_t cap, int k, int32_t *idx_out,
+                         double *d2_out, uint8_t *rgba_out, float *normal_out, void *stream)
+{
+    if (!own_cand || !back || !sel || !count) return PT_ERR_INVALID_ARG;
+    return launch_halo_merge(own_cand, back, sel, count, cap, k, idx_out, d2_out, rgba_out,
+                             normal_out, (cudaStream_t)stream);
+}
+
 // Host-buffer query.  Large batches are cut into chunks that are pipelined over three streams so
 // the H2D copy of the 80-byte records, the kernels and the D2H copy of the results overlap
 // (pinned caller buffers make the copies truly asynchronous; pageable ones still work).

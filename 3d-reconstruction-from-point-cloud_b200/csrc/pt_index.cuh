@@ -77,6 +77,15 @@ int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *
                  double *d2_out, uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
                  cudaStream_t s);
 
+int launch_halo_route(const double *q, const pt_cand *own, uint32_t m, int k, double r2,
+                      const double *boxes, int n_ranks, int self, uint32_t cap, double *send,
+                      int32_t *sel, uint32_t *counts, uint32_t *overflow_flag, cudaStream_t s);
+int launch_halo_prepare(const double *recv, int n_ranks, uint32_t cap, double *q_out, double *r2_out,
+                        cudaStream_t s);
+int launch_halo_merge(pt_cand *own, const pt_cand *back, const int32_t *sel, const uint32_t *count_ptr,
+                      uint32_t cap, int k, int32_t *idx_out, double *d2_out, uint8_t *rgba_out,
+                      float *normal_out, cudaStream_t s);
+
 int  get_option(const char *name, int *value);
 int  set_option(const char *name, int value);
 int  opt_knn_variant();

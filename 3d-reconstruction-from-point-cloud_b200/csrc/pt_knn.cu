@@ -448,4 +448,154 @@ int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *
     return PT_OK;
 }
 
+// ---- halo exchange kernels (multi-GPU) -------------------------------------
+// Fixed-capacity routing so the whole exchange runs without a host synchronisation: every rank
+// keeps, per peer, a send block of (cap + 1) rows of 4 doubles -- row 0 is the header
+// (count, overflow flag), rows 1.. are (x, y, z, bound) of the samples whose k-th-neighbour ball
+// reaches that peer's slab box -- plus the sample index of each row.
+__global__ void __launch_bounds__(256)
+halo_route_kernel(const double *q, const pt_cand *own, uint32_t m, int k, double r2,
+                  const double *boxes, int n_ranks, int self, uint32_t cap, double *send,
+                  int32_t *sel, uint32_t *counts)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m) return;
+    const double x = q[3 * (size_t)s], y = q[3 * (size_t)s + 1], z = q[3 * (size_t)s + 2];
+    const double bound = fmin(own[(size_t)s * k + (k - 1)].d2, r2);   // +inf while the list is short
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == self) continue;
+        const double *b = boxes + 6 * r;
+        const double ex = fmax(fmax(b[0] - x, x - b[3]), 0.0);
+        const double ey = fmax(fmax(b[1] - y, y - b[4]), 0.0);
+        const double ez = fmax(fmax(b[2] - z, z - b[5]), 0.0);
+        // shrunk by 1e-12 relative so rounding can never exclude a slab that holds a neighbour
+        const double lb = (ex * ex + ey * ey + ez * ez) * (1.0 - 1e-12);
+        if (lb <= bound && lb < INFINITY) {   // an empty slab has an inverted box: lb = inf
+            const uint32_t pos = atomicAdd(&counts[r], 1u);
+            if (pos < cap) {
+                double *row = send + ((size_t)r * (cap + 1) + 1 + pos) * 4;
+                row[0] = x; row[1] = y; row[2] = z; row[3] = bound;
+                sel[(size_t)r * cap + pos] = (int32_t)s;
+            }
+        }
+    }
+}
+
+__global__ void halo_header_kernel(const uint32_t *counts, int n_ranks, uint32_t cap, double *send,
+                                   uint32_t *overflow_flag)
+{
+    const int r = threadIdx.x;
+    if (r >= n_ranks) return;
+    const uint32_t c = counts[r];
+    double *row = send + (size_t)r * (cap + 1) * 4;
+    row[0] = (double)(c < cap ? c : cap);
+    row[1] = c > cap ? 1.0 : 0.0;
+    row[2] = 0.0; row[3] = 0.0;
+    if (c > cap) atomicOr(overflow_flag, 1u);
+}
+
+// Received blocks -> query rows for the bounded halo search; rows past a block's count get a
+// negative bound, which the query kernels treat as "no candidates" at once.
+__global__ void __launch_bounds__(256)
+halo_prepare_kernel(const double *recv, int n_ranks, uint32_t cap, double *q_out, double *r2_out)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)n_ranks * cap) return;
+    const uint32_t r = t / cap, j = t % cap;
+    const double *blk = recv + (size_t)r * (cap + 1) * 4;
+    const bool valid = (double)j < blk[0];
+    const double *row = blk + (size_t)(1 + j) * 4;
+    q_out[3 * (size_t)t] = valid ? row[0] : 0.0;
+    q_out[3 * (size_t)t + 1] = valid ? row[1] : 0.0;
+    q_out[3 * (size_t)t + 2] = valid ? row[2] : 0.0;
+    r2_out[t] = valid ? row[3] : -1.0;
+}
+
+// Merges one peer's returned candidate lists into the owner's lists (in place) and re-blends.
+// One warp per routed sample; count_ptr is the device-side number of rows sent to that peer.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+halo_merge_kernel(pt_cand *own, const pt_cand *back, const int32_t *sel, const uint32_t *count_ptr,
+                  uint32_t cap, int k, int32_t *idx_out, double *d2_out, uint8_t *rgba_out,
+                  float *normal_out)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t j = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const uint32_t cnt = min(*count_ptr, cap);
+    if (j >= cnt) return;
+    const uint32_t q = (uint32_t)sel[j];
+    WarpList L;
+    L.d = INFINITY; L.i = IDX_NONE; L.kd = INFINITY; L.ki = IDX_NONE;
+    int src = -1;
+    const pt_cand *lists[2] = {own + (size_t)q * k, back + (size_t)j * k};
+    for (int l = 0; l < 2; ++l) {
+        double d = INFINITY;
+        int id = IDX_NONE;
+        if (lane < (unsigned)k) {
+            d = lists[l][lane].d2;
+            id = lists[l][lane].id;
+            if (id < 0) { id = IDX_NONE; d = INFINITY; }
+        }
+        bool pass = id != IDX_NONE && key_less(d, id, L.kd, L.ki);
+        warp_list_offer(L, src, k, lane, pass, d, id, l * 32 + (int)lane);
+    }
+    const bool has = lane < (unsigned)k && L.i != IDX_NONE;
+    AttrRaw at{0.f, 0.f, 0.f, 0u};
+    if (has) {
+        const pt_cand *c = lists[src >> 5] + (src & 31);
+        at.nx = c->nx; at.ny = c->ny; at.nz = c->nz;
+        at.rgba = (uint32_t)c->r | ((uint32_t)c->g << 8) | ((uint32_t)c->b << 16) | ((uint32_t)c->a << 24);
+    }
+    __syncwarp();   // every lane has read its source record before the in-place update below
+    if (lane < (unsigned)k) {
+        const size_t o = (size_t)q * k + lane;
+        store_cand(own + o, has ? L.d : INFINITY, has ? L.i : -1, at);
+        if (idx_out) idx_out[o] = has ? L.i : -1;
+        if (d2_out) d2_out[o] = has ? L.d : INFINITY;
+    }
+    if (rgba_out || normal_out)
+        warp_blend_store(lane, k, has, L.d, at, rgba_out ? rgba_out + 4 * (size_t)q : nullptr,
+                         normal_out ? normal_out + 3 * (size_t)q : nullptr);
+}
+
+int launch_halo_route(const double *q, const pt_cand *own, uint32_t m, int k, double r2,
+                      const double *boxes, int n_ranks, int self, uint32_t cap, double *send,
+                      int32_t *sel, uint32_t *counts, uint32_t *overflow_flag, cudaStream_t s)
+{
+    if (n_ranks < 1 || n_ranks > 1024 || k < 1 || k > PT_MAX_K) return PT_ERR_INVALID_ARG;
+    PT_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * n_ranks, s));
+    if (m) {
+        halo_route_kernel<<<(m + 255) / 256, 256, 0, s>>>(q, own, m, k, r2, boxes, n_ranks, self, cap,
+                                                         send, sel, counts);
+        count_launch();
+    }
+    halo_header_kernel<<<1, 1024, 0, s>>>(counts, n_ranks, cap, send, overflow_flag);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int launch_halo_prepare(const double *recv, int n_ranks, uint32_t cap, double *q_out, double *r2_out,
+                        cudaStream_t s)
+{
+    const uint32_t total = (uint32_t)n_ranks * cap;
+    if (total == 0) return PT_OK;
+    halo_prepare_kernel<<<(total + 255) / 256, 256, 0, s>>>(recv, n_ranks, cap, q_out, r2_out);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int launch_halo_merge(pt_cand *own, const pt_cand *back, const int32_t *sel, const uint32_t *count_ptr,
+                      uint32_t cap, int k, int32_t *idx_out, double *d2_out, uint8_t *rgba_out,
+                      float *normal_out, cudaStream_t s)
+{
+    if (cap == 0) return PT_OK;
+    if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
+    halo_merge_kernel<<<(cap + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, s>>>(
+        own, back, sel, count_ptr, cap, k, idx_out, d2_out, rgba_out, normal_out);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
 }  // namespace pt

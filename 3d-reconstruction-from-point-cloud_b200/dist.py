@@ -66,6 +66,53 @@ class CudaSlabEngine:
                             normal=out["normal"] if out else None)
         return cand, out
 
+    # ---- fixed-capacity halo exchange (no host synchronisation inside a step) --------------
+    fast = True
+
+    def halo_buffers(self, n_ranks, cap, k):
+        key = (n_ranks, cap, k)
+        if getattr(self, "_halo_key", None) != key:
+            dev = self.device
+            f64, u8, i32 = torch.float64, torch.uint8, torch.int32
+            self._halo = {
+                "send": torch.zeros((n_ranks, cap + 1, 4), dtype=f64, device=dev),
+                "recv": torch.zeros((n_ranks, cap + 1, 4), dtype=f64, device=dev),
+                "sel": torch.zeros((n_ranks, cap), dtype=i32, device=dev),
+                "counts": torch.zeros((n_ranks,), dtype=i32, device=dev),
+                "flag": torch.zeros((1,), dtype=i32, device=dev),
+                "hq": torch.zeros((n_ranks * cap, 3), dtype=f64, device=dev),
+                "hr2": torch.zeros((n_ranks * cap,), dtype=f64, device=dev),
+                "hcand": torch.zeros((n_ranks * cap, k, CAND_BYTES), dtype=u8, device=dev),
+                "back": torch.zeros((n_ranks, cap, k, CAND_BYTES), dtype=u8, device=dev),
+            }
+            self._halo_key = key
+        return self._halo
+
+    def halo_route(self, q, own, k, radius, boxes6, rank, cap, h):
+        api = self._api
+        with torch.cuda.device(self.device):
+            api._check(api.lib().pt_halo_route_device(
+                api._tptr(q), api._tptr(own), q.shape[0], int(k), api._radius(radius),
+                api._tptr(boxes6), boxes6.shape[0], int(rank), int(cap), api._tptr(h["send"]),
+                api._tptr(h["sel"]), api._tptr(h["counts"]), api._tptr(h["flag"]),
+                api._stream_ptr()), "pt_halo_route_device")
+
+    def halo_prepare(self, h, n_ranks, cap):
+        api = self._api
+        with torch.cuda.device(self.device):
+            api._check(api.lib().pt_halo_prepare_device(
+                api._tptr(h["recv"]), int(n_ranks), int(cap), api._tptr(h["hq"]),
+                api._tptr(h["hr2"]), api._stream_ptr()), "pt_halo_prepare_device")
+
+    def halo_merge(self, own, h, r, cap, k, out):
+        api = self._api
+        with torch.cuda.device(self.device):
+            api._check(api.lib().pt_halo_merge_device(
+                api._tptr(own), api._tptr(h["back"][r]), api._tptr(h["sel"][r]),
+                api._tptr(h["counts"][r:r + 1]), int(cap), int(k), api._tptr(out["idx"]),
+                api._tptr(out.get("d2")), api._tptr(out["rgba"]), api._tptr(out["normal"]),
+                api._stream_ptr()), "pt_halo_merge_device")
+
     def merge(self, lists, k, want_d2=False):
         """lists uint8 [R, m, k, 32] -> dict(idx, rgba, normal[, d2])."""
         r, m = lists.shape[0], lists.shape[1]
@@ -115,6 +162,37 @@ class SlabTransfer:
             self.boxes = box[None]
         self.device = dev
         self.stats = {}
+        self.cap = 2048                       # halo rows per peer; doubled after an overflow
+        self.boxes6 = self.boxes.reshape(self.world, 6).contiguous()
+
+    def _transfer_fast(self, q, k, radius, want_d2):
+        """Fixed-capacity exchange on the CUDA engine: route kernel -> all_to_all -> bounded halo
+        search -> all_to_all -> per-peer merge kernels; one deferred overflow check at the end."""
+        eng, R, cap = self.engine, self.world, self.cap
+        own, out = eng.query(q, k, radius=radius, outputs=True, want_d2=want_d2)
+        h = eng.halo_buffers(R, cap, k)
+        h["flag"].zero_()
+        eng.halo_route(q, own, k, radius, self.boxes6, self.rank, cap, h)
+        dist.all_to_all_single(h["recv"].view(R, -1), h["send"].view(R, -1), group=self.group)
+        eng.halo_prepare(h, R, cap)
+        eng.tree.query(h["hq"], k, radius2_per_query=h["hr2"], cand=h["hcand"].view(-1))
+        dist.all_to_all_single(h["back"].view(R, -1), h["hcand"].view(R, -1), group=self.group)
+        for r in range(R):
+            if r != self.rank:
+                eng.halo_merge(own, h, r, cap, k, out)
+        # every rank must take the same path: agree on the overflow flag (one tiny all-reduce,
+        # the only host synchronisation of the step)
+        dist.all_reduce(h["flag"], op=dist.ReduceOp.MAX, group=self.group)
+        if int(h["flag"].item()):             # some peer block did not fit: exact path, larger cap
+            self.cap *= 2
+            return None
+        self._last_counts = h["counts"]
+        return out
+
+    def crossing_count(self):
+        """Samples routed to other slabs in the last fast-path step (synchronises)."""
+        c = getattr(self, "_last_counts", None)
+        return None if c is None else int(c.sum().item())
 
     def _all_to_all(self, send, send_counts, width, dtype):
         """Variable-size exchange of rows ([n, width] tensors ordered by destination rank)."""
@@ -133,6 +211,12 @@ class SlabTransfer:
         Returns dict(idx int32 [m,k] global ids, rgba uint8 [m,4], normal float32 [m,3][, d2])."""
         eng, dev, R = self.engine, self.device, self.world
         m = q.shape[0]
+        if R > 1 and getattr(eng, "fast", False):
+            out = self._transfer_fast(q, k, radius, want_d2)
+            if out is not None:
+                self.stats = {"crossing": None, "sent": None, "received": None, "path": "fast",
+                              "cap": self.cap}
+                return out
         r2 = float("inf") if (radius is None or radius < 0) else float(radius) * float(radius)
         own, out = eng.query(q, k, radius=radius, outputs=True, want_d2=want_d2)   # [m, k, 32]
         if R == 1:
@@ -178,5 +262,5 @@ class SlabTransfer:
             for name, t in merged.items():
                 out[name][cross] = t
         self.stats = {"crossing": nc, "sent": int(sum(send_counts)),
-                      "received": int(sum(recv_counts))}
+                      "received": int(sum(recv_counts)), "path": "exact-size"}
         return out

@@ -310,7 +310,7 @@ def main():
                   "leaves": int(info.n_leaves), "index_bytes": int(info.device_bytes)},
     }
     if slab is not None:
-        line["exchange"] = dict(slab.stats, samples=m)
+        line["exchange"] = dict(slab.stats, samples=m, crossing_fast=slab.crossing_count())
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pto
         P, Q = cpu_window(pkg, pto, pos, attrs, w, args.cpu_window, u0, u1)

@@ -151,6 +151,25 @@ int pt_merge_device(const pt_cand *lists, int n_lists, size_t m, int k,
                     int32_t *idx_out, double *d2_out, uint8_t *rgba_out,
                     float *normal_out, pt_cand *cand_out, int device, void *stream);
 
+/* Halo exchange helpers for slab-sharded clouds.  Fixed-capacity routing,
+ * so the exchange needs no host synchronisation: per peer a send block of (cap + 1) rows of 4
+ * doubles -- row 0 = (count, overflow, 0, 0), rows 1.. = (x, y, z, squared bound) of the samples
+ * whose k-th-neighbour ball reaches that peer's box -- and the sample index of every row.
+ * boxes: n_ranks x 6 doubles (lo xyz, hi xyz).  counts: n_ranks words (reset by the call);
+ * overflow_flag is OR-ed with 1 when a block did not fit (the caller then takes its exact
+ * variable-size path). */
+int pt_halo_route_device(const double *queries_xyz, const pt_cand *own_cand, size_t m, int k,
+                         double radius, const double *boxes, int n_ranks, int self,
+                         uint32_t cap, double *send, int32_t *sel, uint32_t *counts,
+                         uint32_t *overflow_flag, void *stream);
+/* received blocks (n_ranks x (cap+1) x 4) -> query rows + per-row squared bounds (-1 = unused) */
+int pt_halo_prepare_device(const double *recv, int n_ranks, uint32_t cap, double *queries_out,
+                           double *radius2_out, void *stream);
+/* merge one peer's returned lists (cap x k records) into the owner's lists in place + re-blend */
+int pt_halo_merge_device(pt_cand *own_cand, const pt_cand *back, const int32_t *sel,
+                         const uint32_t *count, uint32_t cap, int k, int32_t *idx_out,
+                         double *d2_out, uint8_t *rgba_out, float *normal_out, void *stream);
+
 /* Tuning / introspection. */
 int pt_set_option(const char *name, int value); /* e.g. "knn_variant" */
 int pt_get_option(const char *name, int *value);
