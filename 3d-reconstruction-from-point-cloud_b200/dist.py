@@ -165,7 +165,23 @@ class SlabTransfer:
         self.cap = 2048                       # halo rows per peer; doubled after an overflow
         self.boxes6 = self.boxes.reshape(self.world, 6).contiguous()
 
-    def _transfer_fast(self, q, k, radius, want_d2):
+    def validate(self):
+        """Checks the deferred overflow flags of the steps run with ``validate=False``.
+        Returns True if every such step fitted its halo capacity (its results are exact);
+        otherwise doubles the capacity and returns False (the caller must redo those steps)."""
+        if self.world == 1:
+            return True
+        acc = getattr(self, "_flag_acc", None)
+        if acc is None:
+            return True
+        dist.all_reduce(acc, op=dist.ReduceOp.MAX, group=self.group)
+        bad = int(acc.item())
+        acc.zero_()
+        if bad:
+            self.cap *= 2
+        return not bad
+
+    def _transfer_fast(self, q, k, radius, want_d2, validate=True):
         """Fixed-capacity exchange on the CUDA engine: route kernel -> all_to_all -> bounded halo
         search -> all_to_all -> per-peer merge kernels; one deferred overflow check at the end."""
         eng, R, cap = self.engine, self.world, self.cap
@@ -180,6 +196,12 @@ class SlabTransfer:
         for r in range(R):
             if r != self.rank:
                 eng.halo_merge(own, h, r, cap, k, out)
+        if not validate:                      # deferred: accumulate, checked by validate()
+            if getattr(self, "_flag_acc", None) is None:
+                self._flag_acc = torch.zeros_like(h["flag"])
+            torch.maximum(self._flag_acc, h["flag"], out=self._flag_acc)
+            self._last_counts = h["counts"]
+            return out
         # every rank must take the same path: agree on the overflow flag (one tiny all-reduce,
         # the only host synchronisation of the step)
         dist.all_reduce(h["flag"], op=dist.ReduceOp.MAX, group=self.group)
@@ -206,13 +228,15 @@ class SlabTransfer:
                                input_split_sizes=list(send_counts), group=self.group)
         return recv, recv_counts
 
-    def transfer(self, q, k, radius=None, want_d2=False):
+    def transfer(self, q, k, radius=None, want_d2=False, validate=True):
         """q float64 [m,3] on the engine's device (samples owned by this rank).
-        Returns dict(idx int32 [m,k] global ids, rgba uint8 [m,4], normal float32 [m,3][, d2])."""
+        Returns dict(idx int32 [m,k] global ids, rgba uint8 [m,4], normal float32 [m,3][, d2]).
+        ``validate=False`` (CUDA engine only) skips the per-step overflow agreement, making the
+        step fully asynchronous; the caller must then call ``validate()`` before trusting it."""
         eng, dev, R = self.engine, self.device, self.world
         m = q.shape[0]
         if R > 1 and getattr(eng, "fast", False):
-            out = self._transfer_fast(q, k, radius, want_d2)
+            out = self._transfer_fast(q, k, radius, want_d2, validate)
             if out is not None:
                 self.stats = {"crossing": None, "sent": None, "received": None, "path": "fast",
                               "cap": self.cap}

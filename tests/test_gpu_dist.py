@@ -49,7 +49,15 @@ def _worker(rank, world, port, k, radius):
         assert np.array_equal(out["d2"].cpu().numpy(), ref_d2), f"rank {rank} d2"
         assert np.array_equal(out["rgba"].cpu().numpy(), ref_rgba), f"rank {rank} rgba"
         assert np.allclose(out["normal"].cpu().numpy(), ref_nrm, rtol=1e-5, atol=1e-7)
-        assert st.stats["crossing"] < len(own_q)      # only a sliver is exchanged
+        assert st.stats["path"] == "fast"             # fixed-capacity exchange, no overflow
+        assert st.crossing_count() < len(own_q)       # only a sliver is exchanged
+        # the exact-size path (taken after a capacity overflow) must agree bit for bit
+        st.engine.fast = False
+        out2 = st.transfer(q, k, radius=radius, want_d2=True)
+        torch.cuda.synchronize()
+        assert st.stats["path"] == "exact-size"
+        for name in ("idx", "d2", "rgba", "normal"):
+            assert torch.equal(out[name], out2[name]), name
         tree.close()
     finally:
         dist.destroy_process_group()
