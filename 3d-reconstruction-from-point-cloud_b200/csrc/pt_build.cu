@@ -177,9 +177,59 @@ __device__ __forceinline__ bool kd_after(const Out &a, const Out &b, int axis)
     return ka > kb || (ka == kb && a.idx > b.idx);
 }
 
+template <typename Out>
+__device__ __forceinline__ Out shfl_xor_rec(const Out &v, int lane_mask)
+{
+    Out o;
+    constexpr int W = sizeof(Out) / 4;
+    const int *src = reinterpret_cast<const int *>(&v);
+    int *dst = reinterpret_cast<int *>(&o);
+#pragma unroll
+    for (int w = 0; w < W; ++w) dst[w] = __shfl_xor_sync(0xffffffffu, src[w], lane_mask);
+    return o;
+}
+
+template <typename Out, int E, int J>
+__device__ __forceinline__ void kd_local_step(Out (&r)[E], int i0, int sz, int kk, int ax)
+{
+    if constexpr (J < E) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if ((e & J) == 0) {
+                const bool asc = (((i0 + e) & (sz - 1)) & kk) == 0;
+                if (kd_after(r[e], r[e | J], ax) == asc) { const Out t = r[e]; r[e] = r[e | J]; r[e | J] = t; }
+            }
+        }
+    }
+}
+
+// One bitonic compare-exchange step (stage kk, distance j < 32 E) on the E records a thread
+// holds in registers; records i0 .. i0+E-1 of a segment of size sz sorted along `ax`.
+template <typename Out, int E>
+__device__ __forceinline__ void kd_reg_step(Out (&r)[E], int i0, int sz, int kk, int j, int ax)
+{
+    if (j >= E) {   // partner record e lives in lane ^ (j / E), same slot
+        const bool low = (i0 & j) == 0;
+        const bool asc = ((i0 & (sz - 1)) & kk) == 0;
+        const bool keep_min = low == asc;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const Out p = shfl_xor_rec(r[e], j / E);
+            const bool take = keep_min ? kd_after(r[e], p, ax) : kd_after(p, r[e], ax);
+            if (take) r[e] = p;
+        }
+    } else {        // both records in this thread: static register indices for each j
+        if (j == 4) kd_local_step<Out, E, 4>(r, i0, sz, kk, ax);
+        else if (j == 2) kd_local_step<Out, E, 2>(r, i0, sz, kk, ax);
+        else kd_local_step<Out, E, 1>(r, i0, sz, kk, ax);
+    }
+}
+
 template <typename Out, int BLK>
 __global__ void __launch_bounds__(1024, 1) kd_refine_kernel(Out *pts, uint32_t n_pad)
 {
+    constexpr int E = BLK / 1024;       // records per thread in the register phases
+    constexpr int WSPAN = 32 * E;       // records covered by one warp
     extern __shared__ __align__(16) unsigned char kd_smem[];
     Out *s = reinterpret_cast<Out *>(kd_smem);
     constexpr int MAXSEG = BLK / (2 * LEAF);
@@ -232,18 +282,39 @@ __global__ void __launch_bounds__(1024, 1) kd_refine_kernel(Out *pts, uint32_t n
             seg_axis[tid] = (unsigned char)ax;
         }
         __syncthreads();
-        for (int kk = 2; kk <= sz; kk <<= 1) {
-            for (int j = kk >> 1; j > 0; j >>= 1) {
+        // Bitonic sort of every segment.  A thread owns E consecutive records; compare-exchange
+        // steps whose partner is in the same thread (j < E) or the same warp (j < 32 E) run in
+        // registers / warp shuffles, only the wider ones go through shared memory.
+        const int i0 = tid * E;
+        const int ax = seg_axis[i0 >> shift];
+        const int top_reg = sz < WSPAN ? sz : WSPAN;
+        Out r[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) r[e] = s[i0 + e];
+        for (int kk = 2; kk <= top_reg; kk <<= 1)
+            for (int j = kk >> 1; j > 0; j >>= 1) kd_reg_step<Out, E>(r, i0, sz, kk, j, ax);
+#pragma unroll
+        for (int e = 0; e < E; ++e) s[i0 + e] = r[e];
+        __syncthreads();
+        for (int kk = 2 * WSPAN; kk <= sz; kk <<= 1) {
+            int j = kk >> 1;
+            for (; j >= WSPAN; j >>= 1) {
                 for (int t = tid; t < BLK / 2; t += 1024) {
                     const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const int l = i | j;
-                    const int ax = seg_axis[i >> shift];
+                    const int sax = seg_axis[i >> shift];
                     const bool asc = ((i & (sz - 1)) & kk) == 0;
                     const Out a = s[i], b = s[l];
-                    if (kd_after(a, b, ax) == asc) { s[i] = b; s[l] = a; }
+                    if (kd_after(a, b, sax) == asc) { s[i] = b; s[l] = a; }
                 }
                 __syncthreads();
             }
+#pragma unroll
+            for (int e = 0; e < E; ++e) r[e] = s[i0 + e];
+            for (; j > 0; j >>= 1) kd_reg_step<Out, E>(r, i0, sz, kk, j, ax);
+#pragma unroll
+            for (int e = 0; e < E; ++e) s[i0 + e] = r[e];
+            __syncthreads();
         }
     }
     for (int i = tid; (uint32_t)i < cnt; i += 1024) pts[base + i] = s[i];
