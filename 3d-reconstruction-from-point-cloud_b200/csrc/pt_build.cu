@@ -177,67 +177,67 @@ __device__ __forceinline__ bool kd_after(const Out &a, const Out &b, int axis)
     return ka > kb || (ka == kb && a.idx > b.idx);
 }
 
-template <typename Out>
-__device__ __forceinline__ Out shfl_xor_rec(const Out &v, int lane_mask)
+// ---- sorting (key, position) pairs packed in 64 bits ----------------------------------------
+__device__ __forceinline__ unsigned long long kd_shfl_xor(unsigned long long v, int lane_mask)
 {
-    Out o;
-    constexpr int W = sizeof(Out) / 4;
-    const int *src = reinterpret_cast<const int *>(&v);
-    int *dst = reinterpret_cast<int *>(&o);
-#pragma unroll
-    for (int w = 0; w < W; ++w) dst[w] = __shfl_xor_sync(0xffffffffu, src[w], lane_mask);
-    return o;
+    unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, lane_mask);
+    unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), lane_mask);
+    return ((unsigned long long)hi << 32) | lo;
 }
 
-template <typename Out, int E, int J>
-__device__ __forceinline__ void kd_local_step(Out (&r)[E], int i0, int sz, int kk, int ax)
+// A warp owns 32*E consecutive values of the block, lane-interleaved: slot e of lane l is value
+// wbase + 32*e + l, so shared-memory accesses are conflict-free, compare-exchange distances
+// j < 32 are warp shuffles and distances 32 <= j < 32*E stay inside the thread.
+template <int E, int J>   // J = in-thread slot distance (j / 32)
+__device__ __forceinline__ void kd_local_step(unsigned long long (&r)[E], int ibase, int sz, int kk)
 {
     if constexpr (J < E) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             if ((e & J) == 0) {
-                const bool asc = (((i0 + e) & (sz - 1)) & kk) == 0;
-                if (kd_after(r[e], r[e | J], ax) == asc) { const Out t = r[e]; r[e] = r[e | J]; r[e | J] = t; }
+                const bool asc = (((ibase + 32 * e) & (sz - 1)) & kk) == 0;
+                const unsigned long long a = r[e], b = r[e | J];
+                if ((a > b) == asc) { r[e] = b; r[e | J] = a; }
             }
         }
     }
 }
 
-// One bitonic compare-exchange step (stage kk, distance j < 32 E) on the E records a thread
-// holds in registers; records i0 .. i0+E-1 of a segment of size sz sorted along `ax`.
-template <typename Out, int E>
-__device__ __forceinline__ void kd_reg_step(Out (&r)[E], int i0, int sz, int kk, int j, int ax)
+// One bitonic compare-exchange step (stage kk, distance j < 32 E); ibase = wbase + lane.
+template <int E>
+__device__ __forceinline__ void kd_reg_step(unsigned long long (&r)[E], int ibase, int sz, int kk, int j)
 {
-    if (j >= E) {   // partner record e lives in lane ^ (j / E), same slot
-        const bool low = (i0 & j) == 0;
-        const bool asc = ((i0 & (sz - 1)) & kk) == 0;
-        const bool keep_min = low == asc;
+    if (j < 32) {   // partner = lane ^ j, same slot
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const Out p = shfl_xor_rec(r[e], j / E);
-            const bool take = keep_min ? kd_after(r[e], p, ax) : kd_after(p, r[e], ax);
-            if (take) r[e] = p;
+            const int i = ibase + 32 * e;
+            const bool keep_min = ((i & j) == 0) == (((i & (sz - 1)) & kk) == 0);
+            const unsigned long long p = kd_shfl_xor(r[e], j);
+            r[e] = keep_min ? (p < r[e] ? p : r[e]) : (p > r[e] ? p : r[e]);
         }
-    } else {        // both records in this thread: static register indices for each j
-        if (j == 4) kd_local_step<Out, E, 4>(r, i0, sz, kk, ax);
-        else if (j == 2) kd_local_step<Out, E, 2>(r, i0, sz, kk, ax);
-        else kd_local_step<Out, E, 1>(r, i0, sz, kk, ax);
+    } else {        // both values in this thread: static register indices for each distance
+        if (j == 128) kd_local_step<E, 4>(r, ibase, sz, kk);
+        else if (j == 64) kd_local_step<E, 2>(r, ibase, sz, kk);
+        else kd_local_step<E, 1>(r, ibase, sz, kk);
     }
 }
 
 template <typename Out, int BLK>
 __global__ void __launch_bounds__(1024, 1) kd_refine_kernel(Out *pts, uint32_t n_pad)
 {
-    constexpr int E = BLK / 1024;       // records per thread in the register phases
-    constexpr int WSPAN = 32 * E;       // records covered by one warp
+    constexpr int E = BLK / 1024;       // values per thread
+    constexpr int WSPAN = 32 * E;       // values covered by one warp
     extern __shared__ __align__(16) unsigned char kd_smem[];
     Out *s = reinterpret_cast<Out *>(kd_smem);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(kd_smem + sizeof(Out) * BLK);
     constexpr int MAXSEG = BLK / (2 * LEAF);
     __shared__ int seg_lo[3][MAXSEG], seg_hi[3][MAXSEG];
     __shared__ unsigned char seg_axis[MAXSEG];
     const uint32_t base = blockIdx.x * (uint32_t)BLK;
     const uint32_t cnt = min((uint32_t)BLK, n_pad - base);
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int ibase = (tid >> 5) * WSPAN + lane;      // this thread's slot e is value ibase + 32 e
     for (int i = tid; i < BLK; i += 1024) {
         Out p;
         if ((uint32_t)i < cnt) p = pts[base + i];
@@ -256,14 +256,37 @@ __global__ void __launch_bounds__(1024, 1) kd_refine_kernel(Out *pts, uint32_t n
             for (int a = 0; a < 3; ++a) { seg_lo[a][tid] = 0x7fffffff; seg_hi[a][tid] = (int)0x80000000; }
         }
         __syncthreads();
-        for (int i = tid; i < BLK; i += 1024) {
-            const Out p = s[i];
-            if (p.idx != IDX_NONE) {
-                const int sg = i >> shift;
-                const int ex = ord_f32((float)p.x), ey = ord_f32((float)p.y), ez = ord_f32((float)p.z);
-                atomicMin(&seg_lo[0][sg], ex); atomicMax(&seg_hi[0][sg], ex);
-                atomicMin(&seg_lo[1][sg], ey); atomicMax(&seg_hi[1][sg], ey);
-                atomicMin(&seg_lo[2][sg], ez); atomicMax(&seg_hi[2][sg], ez);
+        // segment bounding boxes: slots of a thread that fall in the same segment are reduced in
+        // registers, then across the warp by shuffles; one lane issues the shared-memory atomics
+        {
+            const int per = sz >= WSPAN ? E : sz / 32;     // consecutive slots per segment
+#pragma unroll
+            for (int g0 = 0; g0 < E; ++g0) {
+                if (g0 % per != 0) continue;
+                int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+                int hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if (e >= g0 && e < g0 + per) {
+                        const Out p = s[ibase + 32 * e];
+                        if (p.idx != IDX_NONE) {
+                            const int ex = ord_f32((float)p.x), ey = ord_f32((float)p.y), ez = ord_f32((float)p.z);
+                            lo[0] = min(lo[0], ex); hi[0] = max(hi[0], ex);
+                            lo[1] = min(lo[1], ey); hi[1] = max(hi[1], ey);
+                            lo[2] = min(lo[2], ez); hi[2] = max(hi[2], ez);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+                    hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+                }
+                if (lane == 0) {
+                    const int sg = (ibase + 32 * g0) >> shift;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { atomicMin(&seg_lo[a][sg], lo[a]); atomicMax(&seg_hi[a][sg], hi[a]); }
+                }
             }
         }
         __syncthreads();
@@ -282,40 +305,50 @@ __global__ void __launch_bounds__(1024, 1) kd_refine_kernel(Out *pts, uint32_t n
             seg_axis[tid] = (unsigned char)ax;
         }
         __syncthreads();
-        // Bitonic sort of every segment.  A thread owns E consecutive records; compare-exchange
-        // steps whose partner is in the same thread (j < E) or the same warp (j < 32 E) run in
-        // registers / warp shuffles, only the wider ones go through shared memory.
-        const int i0 = tid * E;
-        const int ax = seg_axis[i0 >> shift];
+        // Sort (coordinate key, position) pairs of every segment with a bitonic network; the
+        // 16/32-byte records move only once per level.
+        unsigned long long r[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = ibase + 32 * e;
+            const int ax = seg_axis[i >> shift];
+            const Out p = s[i];
+            const float c = (float)(ax == 0 ? p.x : (ax == 1 ? p.y : p.z));
+            unsigned u = __float_as_uint(c);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            if (p.idx == IDX_NONE) u = 0xffffffffu;     // padding sorts last
+            r[e] = ((unsigned long long)u << 32) | (unsigned)i;
+        }
         const int top_reg = sz < WSPAN ? sz : WSPAN;
-        Out r[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) r[e] = s[i0 + e];
         for (int kk = 2; kk <= top_reg; kk <<= 1)
-            for (int j = kk >> 1; j > 0; j >>= 1) kd_reg_step<Out, E>(r, i0, sz, kk, j, ax);
-#pragma unroll
-        for (int e = 0; e < E; ++e) s[i0 + e] = r[e];
-        __syncthreads();
+            for (int j = kk >> 1; j > 0; j >>= 1) kd_reg_step<E>(r, ibase, sz, kk, j);
         for (int kk = 2 * WSPAN; kk <= sz; kk <<= 1) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) keys[ibase + 32 * e] = r[e];
+            __syncthreads();
             int j = kk >> 1;
             for (; j >= WSPAN; j >>= 1) {
                 for (int t = tid; t < BLK / 2; t += 1024) {
                     const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const int l = i | j;
-                    const int sax = seg_axis[i >> shift];
                     const bool asc = ((i & (sz - 1)) & kk) == 0;
-                    const Out a = s[i], b = s[l];
-                    if (kd_after(a, b, sax) == asc) { s[i] = b; s[l] = a; }
+                    const unsigned long long a = keys[i], b = keys[l];
+                    if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
                 }
                 __syncthreads();
             }
 #pragma unroll
-            for (int e = 0; e < E; ++e) r[e] = s[i0 + e];
-            for (; j > 0; j >>= 1) kd_reg_step<Out, E>(r, i0, sz, kk, j, ax);
-#pragma unroll
-            for (int e = 0; e < E; ++e) s[i0 + e] = r[e];
-            __syncthreads();
+            for (int e = 0; e < E; ++e) r[e] = keys[ibase + 32 * e];
+            for (; j > 0; j >>= 1) kd_reg_step<E>(r, ibase, sz, kk, j);
         }
+        // apply the permutation: each position receives the record the sort put there
+        Out rec[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) rec[e] = s[(unsigned)(r[e] & 0xffffffffu)];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e) s[ibase + 32 * e] = rec[e];
+        __syncthreads();
     }
     for (int i = tid; (uint32_t)i < cnt; i += 1024) pts[base + i] = s[i];
 }
@@ -324,7 +357,7 @@ template <typename Out>
 static int kd_refine(Out *pts, uint32_t n_pad, cudaStream_t s)
 {
     constexpr int BLK = sizeof(Out) == 16 ? 8192 : 4096;
-    const size_t smem = (size_t)BLK * sizeof(Out);
+    const size_t smem = (size_t)BLK * (sizeof(Out) + sizeof(unsigned long long));
     PT_CUDA(cudaFuncSetAttribute(kd_refine_kernel<Out, BLK>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kd_refine_kernel<Out, BLK><<<(n_pad + BLK - 1) / BLK, 1024, smem, s>>>(pts, n_pad);
