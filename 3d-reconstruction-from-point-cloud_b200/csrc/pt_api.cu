@@ -13,6 +13,7 @@ namespace pt {
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_verbose{-1};
 static std::atomic<int> g_knn_variant{2};   // 2 thread (default), 1 octet, 0 warp
+static std::atomic<int> g_sort{1};    // 1 hand-written radix sort (default), 0 cub::DeviceRadixSort
 static std::atomic<int> g_order{2};   // 0 Morton, 1 Hilbert, 2 Hilbert + kd refinement (default)
 
 bool verbose()
@@ -40,12 +41,14 @@ int map_cuda_error(cudaError_t e)
 
 int opt_knn_variant() { return g_knn_variant.load(); }
 int opt_order() { return g_order.load(); }
+int opt_sort() { return g_sort.load(); }
 
 int set_option(const char *name, int value)
 {
     if (!name) return PT_ERR_INVALID_ARG;
     if (!strcmp(name, "knn_variant")) { g_knn_variant.store(value); return PT_OK; }
     if (!strcmp(name, "order")) { g_order.store(value); return PT_OK; }
+    if (!strcmp(name, "sort")) { g_sort.store(value); return PT_OK; }
     if (!strcmp(name, "verbose")) { g_verbose.store(value ? 1 : 0); return PT_OK; }
     return PT_ERR_INVALID_ARG;
 }
@@ -54,6 +57,7 @@ int get_option(const char *name, int *value)
     if (!name || !value) return PT_ERR_INVALID_ARG;
     if (!strcmp(name, "knn_variant")) { *value = g_knn_variant.load(); return PT_OK; }
     if (!strcmp(name, "order")) { *value = g_order.load(); return PT_OK; }
+    if (!strcmp(name, "sort")) { *value = g_sort.load(); return PT_OK; }
     if (!strcmp(name, "verbose")) { *value = verbose() ? 1 : 0; return PT_OK; }
     return PT_ERR_INVALID_ARG;
 }

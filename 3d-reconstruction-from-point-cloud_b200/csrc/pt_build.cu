@@ -415,10 +415,25 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const Box *child, uint32_t
     parent[i] = a;
 }
 
-// ---- K2: sort (library radix sort for now; see DESIGN.md "build") ----------------------------
+// ---- K2: sort ------------------------------------------------------------------------------
 static int sort_pairs(unsigned long long *&keys, unsigned long long *keys_alt, uint32_t *&vals,
                       uint32_t *vals_alt, uint32_t n, cudaStream_t s)
 {
+    if (opt_sort() != 0) {   // hand-written LSD radix sort (pt_sort.cu), the default
+        void *ws = nullptr;
+        PT_CUDA(cudaMalloc(&ws, radix_sort_workspace_bytes(n)));
+        unsigned long long *ko = nullptr;
+        uint32_t *vo = nullptr;
+        int rc = radix_sort_pairs(keys, keys_alt, vals, vals_alt, n, 63, ws, s, &ko, &vo);
+        cudaError_t e2 = cudaStreamSynchronize(s);
+        cudaFree(ws);
+        if (rc != PT_OK) return rc;
+        if (e2 != cudaSuccess) return map_cuda_error(e2);
+        keys = ko;
+        vals = vo;
+        return PT_OK;
+    }
+    // library radix sort (CCCL), kept as the reference point the hand-written sort is measured against
     cub::DoubleBuffer<unsigned long long> dk(keys, keys_alt);
     cub::DoubleBuffer<uint32_t> dv(vals, vals_alt);
     size_t tmp_bytes = 0;

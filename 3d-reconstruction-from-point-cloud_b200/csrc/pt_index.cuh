@@ -86,9 +86,15 @@ int launch_halo_merge(pt_cand *own, const pt_cand *back, const int32_t *sel, con
                       uint32_t cap, int k, int32_t *idx_out, double *d2_out, uint8_t *rgba_out,
                       float *normal_out, cudaStream_t s);
 
+size_t radix_sort_workspace_bytes(uint32_t n);
+int radix_sort_pairs(unsigned long long *keys, unsigned long long *keys_alt, uint32_t *vals,
+                     uint32_t *vals_alt, uint32_t n, int bits, void *workspace, cudaStream_t s,
+                     unsigned long long **keys_out, uint32_t **vals_out);
+
 int  get_option(const char *name, int *value);
 int  set_option(const char *name, int value);
 int  opt_knn_variant();
 int  opt_order();
+int  opt_sort();
 
 }  // namespace pt

@@ -1,0 +1,191 @@
+// pt_sort.cu -- K2: hand-written LSD radix sort of (64-bit key, 32-bit index) pairs.
+//
+// Sorts the Morton/Hilbert keys of the cloud.  8-bit digits; one
+// pass = three kernels over tiles of 4096 keys:
+//   rs_hist_kernel    per-tile digit histogram (warp-aggregated shared-memory atomics)
+//                     -> counts[digit][tile]
+//   rs_scan_kernel    per digit, exclusive prefix over the tiles (block scan + carry), digit totals
+//   rs_scatter_kernel stable in-tile ranking with __match_any_sync (a warp walks its 512 keys in
+//                     16 coalesced rounds; ranks = digit base + tile prefix + preceding warps of
+//                     the tile + preceding rounds + lower lanes with the same digit), scatter
+// Bytes moved per pass: 8 (hist read) + 12 (scatter read) + 12 (scatter write) per pair.
+// HBM-bound by design; cub::DeviceRadixSort (CCCL, one-sweep) is the number it is compared
+// against in profiles/ (pt_set_option("sort", 0) selects the library call for that comparison).
+#include "pt_index.cuh"
+
+namespace pt {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 16;                       // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;     // 4096
+constexpr int RS_RADIX = 256;
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const unsigned long long *keys, uint32_t n, int shift, uint32_t num_tiles,
+               uint32_t *counts)
+{
+    __shared__ uint32_t h[RS_RADIX];
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    h[tid] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * (uint32_t)RS_TILE;
+#pragma unroll 4
+    for (int it = 0; it < RS_ROUNDS; ++it) {
+        const uint32_t i = base + it * RS_THREADS + tid;
+        const bool valid = i < n;
+        const unsigned d = valid ? (unsigned)((keys[i] >> shift) & 0xffu) : 0x100u;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (valid && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    counts[(size_t)tid * num_tiles + blockIdx.x] = h[tid];
+}
+
+// One block per digit: exclusive prefix of counts[digit][0..num_tiles) in place, total out.
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scan_kernel(uint32_t *counts, uint32_t num_tiles, uint32_t *totals)
+{
+    __shared__ uint32_t warp_sum[RS_WARPS];
+    __shared__ uint32_t carry_s;
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t *row = counts + (size_t)blockIdx.x * num_tiles;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < num_tiles; t0 += RS_THREADS) {
+        const uint32_t t = t0 + tid;
+        const uint32_t v = t < num_tiles ? row[t] : 0;
+        uint32_t x = v;                                  // inclusive warp scan
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, s);
+            if (lane >= (unsigned)s) x += y;
+        }
+        if (lane == 31) warp_sum[w] = x;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int j = 0; j < RS_WARPS; ++j) wbase += j < (int)w ? warp_sum[j] : 0;
+        const uint32_t carry = carry_s;
+        if (t < num_tiles) row[t] = carry + wbase + x - v;
+        __syncthreads();
+        if (tid == RS_THREADS - 1) carry_s = carry + wbase + x;
+        __syncthreads();
+    }
+    if (tid == 0) totals[blockIdx.x] = carry_s;
+}
+
+__global__ void __launch_bounds__(RS_RADIX) rs_base_kernel(const uint32_t *totals, uint32_t *bases)
+{
+    __shared__ uint32_t s[RS_RADIX];
+    const unsigned tid = threadIdx.x;
+    s[tid] = totals[tid];
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int d = 0; d < RS_RADIX; ++d) { uint32_t v = s[d]; s[d] = acc; acc += v; }
+    }
+    __syncthreads();
+    bases[tid] = s[tid];
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const unsigned long long *keys_in, const uint32_t *vals_in,
+                  unsigned long long *keys_out, uint32_t *vals_out, uint32_t n, int shift,
+                  uint32_t num_tiles, const uint32_t *counts, const uint32_t *bases)
+{
+    __shared__ uint32_t whist[RS_WARPS][RS_RADIX];   // per-warp digit counts, then running offsets
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int j = tid; j < RS_WARPS * RS_RADIX; j += RS_THREADS) (&whist[0][0])[j] = 0;
+    __syncthreads();
+    // warp w owns keys [w*512, w*512+512) of the tile, 16 coalesced rounds of 32
+    const uint32_t wbase = blockIdx.x * (uint32_t)RS_TILE + w * (32 * RS_ROUNDS);
+    unsigned long long key[RS_ROUNDS];
+    uint32_t val[RS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        key[r] = i < n ? keys_in[i] : ~0ull;
+        val[r] = i < n ? vals_in[i] : 0u;
+    }
+    // 1. per-warp histogram
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool valid = i < n;
+        const unsigned d = valid ? (unsigned)((key[r] >> shift) & 0xffu) : 0x100u;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (valid && lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += (uint32_t)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // 2. digit d: global base + this tile's prefix + the preceding warps of the tile
+    {
+        const unsigned d = tid;
+        uint32_t off = bases[d] + counts[(size_t)d * num_tiles + blockIdx.x];
+#pragma unroll
+        for (int j = 0; j < RS_WARPS; ++j) {
+            const uint32_t c = whist[j][d];
+            whist[j][d] = off;
+            off += c;
+        }
+    }
+    __syncthreads();
+    // 3. stable ranks and scatter
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool valid = i < n;
+        const unsigned d = valid ? (unsigned)((key[r] >> shift) & 0xffu) : 0x100u;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        uint32_t pos = 0;
+        if (valid) {
+            pos = whist[w][d] + (uint32_t)__popc(peers & lt);
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+        __syncwarp();
+        if (valid && lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += (uint32_t)__popc(peers);
+        __syncwarp();
+    }
+}
+
+size_t radix_sort_workspace_bytes(uint32_t n)
+{
+    const uint32_t num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    return sizeof(uint32_t) * ((size_t)RS_RADIX * num_tiles + 2 * RS_RADIX);
+}
+
+// Sorts pairs by the low `bits` bits of the key.  Ping-pongs between (keys, vals) and
+// (keys_alt, vals_alt); on return *keys_out / *vals_out point at the buffers holding the result.
+int radix_sort_pairs(unsigned long long *keys, unsigned long long *keys_alt, uint32_t *vals,
+                     uint32_t *vals_alt, uint32_t n, int bits, void *workspace, cudaStream_t s,
+                     unsigned long long **keys_out, uint32_t **vals_out)
+{
+    *keys_out = keys;
+    *vals_out = vals;
+    if (n == 0) return PT_OK;
+    const uint32_t num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t *counts = (uint32_t *)workspace;
+    uint32_t *totals = counts + (size_t)RS_RADIX * num_tiles;
+    uint32_t *bases = totals + RS_RADIX;
+    unsigned long long *kin = keys, *kout = keys_alt;
+    uint32_t *vin = vals, *vout = vals_alt;
+    for (int shift = 0; shift < bits; shift += 8) {
+        rs_hist_kernel<<<num_tiles, RS_THREADS, 0, s>>>(kin, n, shift, num_tiles, counts);
+        rs_scan_kernel<<<RS_RADIX, RS_THREADS, 0, s>>>(counts, num_tiles, totals);
+        rs_base_kernel<<<1, RS_RADIX, 0, s>>>(totals, bases);
+        rs_scatter_kernel<<<num_tiles, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, num_tiles,
+                                                         counts, bases);
+        count_launch(4);
+        unsigned long long *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
+    }
+    PT_CUDA(cudaGetLastError());
+    *keys_out = kin;
+    *vals_out = vin;
+    return PT_OK;
+}
+
+}  // namespace pt

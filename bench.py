@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--variant", type=int, default=-1, help="knn kernel variant (tuning)")
     ap.add_argument("--order", type=int, default=-1, help="0 Morton, 1 Hilbert (tuning)")
+    ap.add_argument("--sort", type=int, default=-1, help="1 hand-written radix sort, 0 CUB (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-window", type=float, default=0.25,
                     help="side fraction of the domain used for the bounded CPU sample")
@@ -184,6 +185,8 @@ def main():
         pkg.set_option("knn_variant", args.variant)
     if args.order >= 0:
         pkg.set_option("order", args.order)
+    if args.sort >= 0:
+        pkg.set_option("sort", args.sort)
 
     w, n, gu, gv, k = resolve_workload(args, pkg)
     L = pkg.synth.L_DOMAIN
