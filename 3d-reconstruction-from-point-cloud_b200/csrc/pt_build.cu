@@ -11,6 +11,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 
 #include "pt_index.cuh"
@@ -417,18 +418,13 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const Box *child, uint32_t
 
 // ---- K2: sort ------------------------------------------------------------------------------
 static int sort_pairs(unsigned long long *&keys, unsigned long long *keys_alt, uint32_t *&vals,
-                      uint32_t *vals_alt, uint32_t n, cudaStream_t s)
+                      uint32_t *vals_alt, uint32_t n, void *ws, cudaStream_t s)
 {
     if (opt_sort() != 0) {   // hand-written LSD radix sort (pt_sort.cu), the default
-        void *ws = nullptr;
-        PT_CUDA(cudaMalloc(&ws, radix_sort_workspace_bytes(n)));
         unsigned long long *ko = nullptr;
         uint32_t *vo = nullptr;
         int rc = radix_sort_pairs(keys, keys_alt, vals, vals_alt, n, 63, ws, s, &ko, &vo);
-        cudaError_t e2 = cudaStreamSynchronize(s);
-        cudaFree(ws);
         if (rc != PT_OK) return rc;
-        if (e2 != cudaSuccess) return map_cuda_error(e2);
         keys = ko;
         vals = vo;
         return PT_OK;
@@ -458,6 +454,15 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
 {
     cudaStream_t s = ix->stream;
     PT_CUDA(cudaEventRecord(ix->ev[0], s));
+    auto wall0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {   // PT_VERBOSE=1: host wall-clock per build phase
+        if (!verbose()) return;
+        cudaStreamSynchronize(s);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[points_transfer] build %-18s %8.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(now - wall0).count());
+        wall0 = now;
+    };
     ix->n = n;
     ix->n_leaves = cdiv(n, LEAF);
     ix->coord_f64 = sizeof(Out) == 32;
@@ -495,20 +500,28 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     if (!std::isfinite(kp.inv_cell)) kp.inv_cell = 0.0;
     kp.order = opt_order();
 
+    lap("bbox");
     // K1: keys, K2: sort
     unsigned long long *keys = nullptr, *keys_alt = nullptr;
     uint32_t *vals = nullptr, *vals_alt = nullptr;
-    PT_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)n));
-    PT_CUDA(cudaMalloc(&keys_alt, sizeof(unsigned long long) * (size_t)n));
-    PT_CUDA(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)n));
-    PT_CUDA(cudaMalloc(&vals_alt, sizeof(uint32_t) * (size_t)n));
-    unsigned long long *keys0 = keys;
-    uint32_t *vals0 = vals;
+    // one arena for all sort temporaries (cudaMalloc costs milliseconds per call)
+    const size_t kbytes = (sizeof(unsigned long long) * (size_t)n + 255) & ~(size_t)255;
+    const size_t vbytes = (sizeof(uint32_t) * (size_t)n + 255) & ~(size_t)255;
+    char *arena = nullptr;
+    PT_CUDA(cudaMalloc(&arena, 2 * kbytes + 2 * vbytes + radix_sort_workspace_bytes(n)));
+    keys = (unsigned long long *)arena;
+    keys_alt = (unsigned long long *)(arena + kbytes);
+    vals = (uint32_t *)(arena + 2 * kbytes);
+    vals_alt = (uint32_t *)(arena + 2 * kbytes + vbytes);
+    void *sort_ws = arena + 2 * kbytes + 2 * vbytes;
+    lap("alloc keys");
     morton_kernel<In><<<cdiv(n, 256), 256, 0, s>>>(in, n, kp, keys, vals);
     count_launch();
-    int rc = sort_pairs(keys, keys_alt, vals, vals_alt, n, s);
+    lap("keys");
+    int rc = sort_pairs(keys, keys_alt, vals, vals_alt, n, sort_ws, s);
+    lap("sort");
     if (rc != PT_OK) {
-        cudaFree(keys0); cudaFree(keys_alt); cudaFree(vals0); cudaFree(vals_alt);
+        cudaFree(arena);
         return rc;
     }
 
@@ -519,7 +532,9 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     gather_kernel<In, Out><<<cdiv(n_pad, 256), 256, 0, s>>>(in, vals, n, (uint32_t)n_pad, pts);
     count_launch();
     ix->pts = pts;
+    lap("gather");
     if (kp.order == 2) PT_TRY(kd_refine<Out>(pts, (uint32_t)n_pad, s));
+    lap("kd refine");
 
     // box pyramid
     uint64_t total = 0;
@@ -557,8 +572,9 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
 
     PT_CUDA(cudaEventRecord(ix->ev[1], s));
     PT_CUDA(cudaStreamSynchronize(s));
+    lap("boxes");
     PT_CUDA(cudaEventElapsedTime(&ix->build_ms, ix->ev[0], ix->ev[1]));
-    cudaFree(keys0); cudaFree(keys_alt); cudaFree(vals0); cudaFree(vals_alt);
+    cudaFree(arena);
     ix->device_bytes = sizeof(Out) * n_pad + sizeof(Box) * total +
                        (ix->attrs ? sizeof(pt_attr) * (size_t)n : 0) +
                        (ix->ids ? sizeof(int32_t) * (size_t)n : 0);

@@ -6,7 +6,7 @@
 //                     -> counts[digit][tile]
 //   rs_scan_kernel    per digit, exclusive prefix over the tiles (block scan + carry), digit totals
 //   rs_scatter_kernel stable in-tile ranking with __match_any_sync (a warp walks its 512 keys in
-//                     16 coalesced rounds; ranks = digit base + tile prefix + preceding warps of
+//                     RS_ROUNDS coalesced rounds; ranks = digit base + tile prefix + preceding warps of
 //                     the tile + preceding rounds + lower lanes with the same digit), scatter
 // Bytes moved per pass: 8 (hist read) + 12 (scatter read) + 12 (scatter write) per pair.
 // HBM-bound by design; cub::DeviceRadixSort (CCCL, one-sweep) is the number it is compared
@@ -17,7 +17,10 @@ namespace pt {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ROUNDS = 16;                       // keys per thread
+#ifndef PT_RS_ROUNDS
+#define PT_RS_ROUNDS 8
+#endif
+constexpr int RS_ROUNDS = PT_RS_ROUNDS;             // keys per thread
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;     // 4096
 constexpr int RS_RADIX = 256;
 
