@@ -295,3 +295,39 @@ def test_full_size_properties(pkg, pto, torch_cuda):
         assert np.array_equal(ids[ridx[0]], idx[s].cpu().numpy())
         assert np.array_equal(rd2[0], d2[s].cpu().numpy())
     tree.close()
+
+
+@pytest.mark.parametrize("cfg,n,g,k", [("cfg5", 1_500_000, 120, 16), ("cfg4", 1_000_000, 128, 32),
+                                       ("cfg1", 1_000_000, 100, 8)])
+def test_baseline_config_shapes_vs_oracle(cfg, n, g, k, pkg, pto, torch_cuda):
+    """BASELINE.json configs at oracle-checkable sizes, generated by the same device generators
+    the bench uses: cfg5 = skewed clusters + radius-bounded (short / empty lists expected),
+    cfg4 = texel-centre samples with k = 32, cfg1 = the reference's CPU-runnable case in full."""
+    torch = torch_cuda
+    w = pkg.synth.CONFIGS[cfg]
+    side = 1000.0 if cfg == "cfg1" else 150.0
+    pos, attrs = pkg.synth.cloud_device(n, w.seed, u1=side, v1=side, kind=w.kind, sigma=w.sigma
+                                        if cfg != "cfg5" else side / 2000.0)
+    q = pkg.synth.samples_device(g, g, u1=side, v1=side, center=w.center)
+    radius = None if w.radius is None else w.radius * (side / 1000.0) * 4
+    P = pkg.synth.points_to_host(pos, attrs)
+    Q = pkg.synth.queries_to_host(q)
+    ref_idx, ref_d2 = pto.KdTree(P).knn(Q, k, radius=-1.0 if radius is None else radius)
+    ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+    for variant in (2, 0):
+        pkg.set_option("knn_variant", variant)
+        tree = pkg.DeviceTree(pos, attrs)
+        m = q.shape[0]
+        idx = torch.empty((m, k), dtype=torch.int32, device="cuda")
+        d2 = torch.empty((m, k), dtype=torch.float64, device="cuda")
+        rgba = torch.empty((m, 4), dtype=torch.uint8, device="cuda")
+        nrm = torch.empty((m, 3), dtype=torch.float32, device="cuda")
+        tree.query(q, k, radius=radius, idx=idx, d2=d2, rgba=rgba, normal=nrm)
+        torch.cuda.synchronize()
+        tree.close()
+        assert np.array_equal(idx.cpu().numpy(), ref_idx), (cfg, variant)
+        assert np.array_equal(d2.cpu().numpy(), ref_d2), (cfg, variant)
+        _check_blend(rgba.cpu().numpy(), nrm.cpu().numpy(), ref_rgba, ref_nrm)
+    if cfg == "cfg5":
+        short = (ref_idx < 0).any(axis=1).mean()
+        assert 0.05 < short < 1.0      # the radius bound really bites on the sparse part
