@@ -15,6 +15,8 @@
 // instead of texture.png the tool writes `transferred.ply`, the input mesh in the same 11-column
 // ASCII format with the transferred colour and normal per vertex.  Extra options (all default to
 // the reference's behaviour): -k N, -r RADIUS, -o FILE, -d DEVICE.
+#include <algorithm>
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +25,7 @@
 #include <iostream>
 #include <iterator>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "points_transfer.h"
@@ -47,9 +50,15 @@ struct Tokens {
     size_t pos = 0;
     bool load(const std::string &path)
     {
-        std::ifstream f(path, std::ios::in | std::ios::binary);
-        if (!f.is_open()) return false;
-        buf.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) return false;
+        fseek(f, 0, SEEK_END);
+        long size = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        buf.resize(size > 0 ? (size_t)size : 0);
+        size_t got = size > 0 ? fread(&buf[0], 1, (size_t)size, f) : 0;
+        fclose(f);
+        buf.resize(got);
         return true;
     }
     bool next(const char *&b, const char *&e)
@@ -108,6 +117,107 @@ bool read_rows(Tokens &t, long count, int columns, std::vector<Point> &out)
     return true;
 }
 
+// ---- fast path: line-parallel body parser ---------------------------
+// Standard ASCII PLY puts one element per line.  The body is cut into byte ranges at line
+// boundaries, every thread counts its non-empty lines, a prefix sum gives each thread its first
+// record number, then the threads parse their lines straight into the output arrays with
+// std::from_chars (correctly rounded, i.e. the same doubles atof produces at :207 etc.).
+// Returns false (caller falls back to the sequential token parser, which accepts any
+// whitespace layout like the reference does) if the file is not one-record-per-line.
+inline const char *skip_ws(const char *p, const char *e)
+{
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+    return p;
+}
+
+inline bool parse_num(const char *&p, const char *e, double &v)
+{
+    p = skip_ws(p, e);
+    if (p < e && *p == '+') ++p;          // from_chars rejects a leading '+', atof accepts it
+    auto r = std::from_chars(p, e, v);
+    if (r.ec != std::errc()) return false;
+    p = r.ptr;
+    return true;
+}
+
+bool parse_body_parallel(const std::string &buf, size_t body, long n_vertex, int columns, long n_face,
+                         std::vector<Point> &vertices, std::vector<int> *faces)
+{
+    const char *b = buf.data() + body, *e = buf.data() + buf.size();
+    const long want = n_vertex + (faces ? n_face : 0);
+    if (n_vertex < 0 || want <= 0) return false;
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if ((size_t)(e - b) < (size_t)nt * 65536) nt = 1;
+    std::vector<const char *> lo(nt + 1);
+    for (unsigned t = 0; t <= nt; ++t) {
+        const char *p = b + (size_t)(e - b) * t / nt;
+        if (t > 0 && t < nt) {               // advance to the start of the next line
+            while (p < e && p[-1] != '\n') ++p;
+        }
+        lo[t] = t == nt ? e : p;
+    }
+    auto non_empty = [](const char *p, const char *q) {
+        for (; p < q; ++p) if (*p != ' ' && *p != '\t' && *p != '\r') return true;
+        return false;
+    };
+    std::vector<long> first(nt + 1, 0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t] {
+                long c = 0;
+                for (const char *p = lo[t]; p < lo[t + 1];) {
+                    const char *nl = (const char *)memchr(p, '\n', lo[t + 1] - p);
+                    const char *q = nl ? nl : lo[t + 1];
+                    if (non_empty(p, q)) ++c;
+                    p = q + 1;
+                }
+                first[t + 1] = c;
+            });
+        for (auto &x : th) x.join();
+    }
+    for (unsigned t = 0; t < nt; ++t) first[t + 1] += first[t];
+    if (first[nt] < want) return false;       // fewer lines than records: not line-structured
+    vertices.assign((size_t)n_vertex, Point());
+    if (faces) faces->assign((size_t)n_face * 3, 0);
+    std::vector<char> ok(nt, 1);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t] {
+                long rec = first[t];
+                for (const char *p = lo[t]; p < lo[t + 1] && rec < want;) {
+                    const char *nl = (const char *)memchr(p, '\n', lo[t + 1] - p);
+                    const char *q = nl ? nl : lo[t + 1];
+                    if (non_empty(p, q)) {
+                        const char *c = p;
+                        double row[11];
+                        if (rec < n_vertex) {
+                            for (int k = 0; k < columns; ++k)
+                                if (!parse_num(c, q, row[k])) { ok[t] = 0; return; }
+                            Point &v = vertices[(size_t)rec];
+                            v.ver[0] = row[0]; v.ver[1] = row[1]; v.ver[2] = row[2];
+                            v.normal[0] = row[3]; v.normal[1] = row[4]; v.normal[2] = row[5];
+                            int c0 = 6;
+                            if (columns == 11) { v.U = row[6]; v.V = row[7]; c0 = 8; }
+                            v.color[0] = (int)row[c0]; v.color[1] = (int)row[c0 + 1]; v.color[2] = (int)row[c0 + 2];
+                        } else {
+                            for (int k = 0; k < 4; ++k)
+                                if (!parse_num(c, q, row[k])) { ok[t] = 0; return; }
+                            int *f = faces->data() + 3 * (size_t)(rec - n_vertex);
+                            f[0] = (int)row[1]; f[1] = (int)row[2]; f[2] = (int)row[3];
+                        }
+                        ++rec;
+                    }
+                    p = q + 1;
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    for (char c : ok) if (!c) return false;
+    return true;
+}
+
 void memory_report()
 {
     long virt = 0, res = 0;
@@ -155,7 +265,10 @@ int main(int argc, char **argv)
     read_header(pc, ph);
     std::cout << "PC Point count: " << ph.vertex << std::endl;
     std::vector<Point> points;
-    read_rows(pc, ph.vertex, 9, points);
+    if (!parse_body_parallel(pc.buf, pc.pos, ph.vertex, 9, 0, points, nullptr)) {
+        points.clear();
+        read_rows(pc, ph.vertex, 9, points);      // any-whitespace layout, like the reference
+    }
     std::cout << "Read point set in: " << task_timer.time() << " seconds" << std::endl;
     task_timer.reset();
 
@@ -183,13 +296,17 @@ int main(int argc, char **argv)
     std::cout << "Mesh vertex count: " << mh.vertex << std::endl;
     std::cout << "Mesh face count: " << mh.face << std::endl;
     std::vector<Point> vertices;
-    read_rows(mesh, mh.vertex, 11, vertices);
     std::vector<int> faces;   // heap, not the reference's stack VLA (:406)
-    faces.reserve(mh.face > 0 ? 3 * mh.face : 0);
-    for (long f = 0; f < mh.face; ++f) {
-        double cnt, a, b, c;
-        if (!mesh.next_double(cnt) || !mesh.next_double(a) || !mesh.next_double(b) || !mesh.next_double(c)) break;
-        faces.push_back((int)a); faces.push_back((int)b); faces.push_back((int)c);
+    if (!parse_body_parallel(mesh.buf, mesh.pos, mh.vertex, 11, mh.face < 0 ? 0 : mh.face, vertices, &faces)) {
+        vertices.clear();
+        faces.clear();
+        read_rows(mesh, mh.vertex, 11, vertices);
+        faces.reserve(mh.face > 0 ? 3 * mh.face : 0);
+        for (long f = 0; f < mh.face; ++f) {
+            double cnt, a, b, c;
+            if (!mesh.next_double(cnt) || !mesh.next_double(a) || !mesh.next_double(b) || !mesh.next_double(c)) break;
+            faces.push_back((int)a); faces.push_back((int)b); faces.push_back((int)c);
+        }
     }
     std::cout << "Read mesh faces: " << task_timer.time() << " seconds" << std::endl;
     task_timer.reset();
