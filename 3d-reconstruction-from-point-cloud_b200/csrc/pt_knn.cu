@@ -148,6 +148,9 @@ __device__ __forceinline__ double shfl_f64(double v, int src)
 
 // Offer one candidate per lane (pass = lane has a candidate that beats the k-th entry).
 // `tag` rides along with the entry (merge kernel: where the candidate came from).
+// DEDUPE: skip a candidate whose id is already in the list (slab indexes that carry ghost
+// points can return the same global point from two ranks).
+template <bool DEDUPE = false>
 __device__ __forceinline__ void warp_list_offer(WarpList &L, int &tag_list, int k, unsigned lane,
                                                 bool pass, double d, int idx, int tag)
 {
@@ -159,6 +162,7 @@ __device__ __forceinline__ void warp_list_offer(WarpList &L, int &tag_list, int 
         int ci = __shfl_sync(0xffffffffu, idx, c);
         int ct = __shfl_sync(0xffffffffu, tag, c);
         if (!key_less(cd, ci, L.kd, L.ki)) continue;  // threshold moved since the ballot
+        if (DEDUPE && __any_sync(0xffffffffu, L.i == ci)) continue;
         unsigned before = __ballot_sync(0xffffffffu, key_less(L.d, L.i, cd, ci));
         unsigned pos = __popc(before);
         double ud = __shfl_up_sync(0xffffffffu, L.d, 1);
@@ -414,7 +418,7 @@ merge_kernel(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *idx_
             if (id < 0) { id = IDX_NONE; d = INFINITY; }
         }
         bool pass = id != IDX_NONE && key_less(d, id, L.kd, L.ki);
-        warp_list_offer(L, src, k, lane, pass, d, id, l * 32 + (int)lane);
+        warp_list_offer<true>(L, src, k, lane, pass, d, id, l * 32 + (int)lane);
     }
     bool has = lane < (unsigned)k && L.i != IDX_NONE;
     AttrRaw at{0.f, 0.f, 0.f, 0u};
@@ -536,7 +540,7 @@ halo_merge_kernel(pt_cand *own, const pt_cand *back, const int32_t *sel, const u
             if (id < 0) { id = IDX_NONE; d = INFINITY; }
         }
         bool pass = id != IDX_NONE && key_less(d, id, L.kd, L.ki);
-        warp_list_offer(L, src, k, lane, pass, d, id, l * 32 + (int)lane);
+        warp_list_offer<true>(L, src, k, lane, pass, d, id, l * 32 + (int)lane);
     }
     const bool has = lane < (unsigned)k && L.i != IDX_NONE;
     AttrRaw at{0.f, 0.f, 0.f, 0u};

@@ -45,12 +45,13 @@ class CudaSlabEngine:
         self.bbox_lo = torch.tensor(list(info.bbox_lo), dtype=torch.float64, device=dev)
         self.bbox_hi = torch.tensor(list(info.bbox_hi), dtype=torch.float64, device=dev)
 
-    def query(self, q, k, radius=None, radius2_per_query=None, outputs=False, want_d2=False):
+    def query(self, q, k, radius=None, radius2_per_query=None, outputs=False, want_d2=False,
+              want_cand=True):
         """-> (cand uint8 [m, k, 32] pt_cand records (d2, global id, attributes), out) where
         out is None or, with ``outputs``, the fused-blend results of the same launch."""
         m = q.shape[0]
         dev = q.device
-        cand = torch.empty((m, k, CAND_BYTES), dtype=torch.uint8, device=dev)
+        cand = torch.empty((m, k, CAND_BYTES), dtype=torch.uint8, device=dev) if want_cand else None
         out = None
         if outputs:
             out = {"idx": torch.empty((m, k), dtype=torch.int32, device=dev),
@@ -60,7 +61,8 @@ class CudaSlabEngine:
                 out["d2"] = torch.empty((m, k), dtype=torch.float64, device=dev)
         if m:
             self.tree.query(q, k, radius=radius, radius2_per_query=radius2_per_query,
-                            cand=cand.view(-1), idx=out["idx"] if out else None,
+                            cand=cand.view(-1) if want_cand else None,
+                            idx=out["idx"] if out else None,
                             d2=out.get("d2") if out else None,
                             rgba=out["rgba"] if out else None,
                             normal=out["normal"] if out else None)
@@ -141,16 +143,85 @@ def empty_cand(shape, device):
     return c
 
 
-class SlabTransfer:
-    """Collective detail transfer: every rank calls ``transfer`` with the samples it owns."""
+def points_box(xyz):
+    """[2,3] float64 bounding box of xyz[n,>=3] (inverted when empty)."""
+    if xyz.shape[0] == 0:
+        return torch.tensor([[float("inf")] * 3, [float("-inf")] * 3], dtype=torch.float64,
+                            device=xyz.device)
+    p = xyz[:, :3].to(torch.float64)
+    return torch.stack([p.min(dim=0).values, p.max(dim=0).values])
 
-    def __init__(self, engine, group=None):
+
+def gather_boxes(box, group=None):
+    """all_gather of every rank's [2,3] box -> [R,2,3]."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return box[None].clone()
+    boxes = [torch.empty_like(box) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(boxes, box.contiguous(), group=group)
+    return torch.stack(boxes)
+
+
+def exchange_ghosts(pos, attrs, ids, boxes, halo, group=None):
+    """Build-time ghost-zone exchange (north_star: "a spatial slab of the cloud plus a halo sized
+    to the search radius").  Every rank sends each peer its own points that lie within ``halo``
+    of that peer's slab box and receives the peers' points near its own box.  Returns the
+    augmented (pos, attrs, ids), sorted by global id so that local tie-breaking stays global.
+    pos [n,4], attrs [n,16] uint8, ids [n] int32 (strictly increasing)."""
+    R = dist.get_world_size(group) if dist.is_initialized() else 1
+    if R == 1:
+        return pos, attrs, ids
+    rank = dist.get_rank(group)
+    dev = pos.device
+    xyz = pos[:, :3].to(torch.float64)
+    h2 = float(halo) * float(halo) * (1.0 + 1e-9)
+    send_idx, counts = [], []
+    for r in range(R):
+        if r == rank or pos.shape[0] == 0:
+            sel = torch.empty((0,), dtype=torch.int64, device=dev)
+        else:
+            e = torch.clamp(torch.maximum(boxes[r, 0] - xyz, xyz - boxes[r, 1]), min=0.0)
+            sel = torch.nonzero((e * e).sum(dim=1) <= h2).view(-1)
+        send_idx.append(sel)
+        counts.append(int(sel.numel()))
+    order = torch.cat(send_idx)
+    sc = torch.tensor(counts, dtype=torch.int64, device=dev)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    rcl = rc.tolist()
+
+    def a2a(t):
+        out = torch.empty((sum(rcl),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        dist.all_to_all_single(out, t[order].contiguous(), output_split_sizes=rcl,
+                               input_split_sizes=counts, group=group)
+        return out
+
+    g_pos, g_attr, g_ids = a2a(pos), a2a(attrs), a2a(ids)
+    all_ids = torch.cat([ids, g_ids])
+    perm = torch.argsort(all_ids)
+    return (torch.cat([pos, g_pos])[perm].contiguous(),
+            torch.cat([attrs, g_attr])[perm].contiguous(), all_ids[perm].contiguous())
+
+
+class SlabTransfer:
+    """Collective detail transfer: every rank calls ``transfer`` with the samples it owns.
+
+    With ``own_box`` and ``halo`` (index built over the slab plus the ghost zone returned by
+    ``exchange_ghosts``) a sample is final as soon as ``dist(q, own_box) + r_k <= halo`` -- every
+    point that could matter is local -- so the steady state needs no collective at all; samples
+    that violate the bound make the step fall back to the per-step halo exchange."""
+
+    def __init__(self, engine, group=None, own_box=None, halo=None):
         self.engine = engine
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         dev = engine.device
-        box = torch.stack([engine.bbox_lo, engine.bbox_hi]).to(torch.float64)
+        self.halo = None if halo is None else float(halo)
+        if own_box is not None:
+            box = own_box.to(torch.float64).to(dev)
+        else:
+            box = torch.stack([engine.bbox_lo, engine.bbox_hi]).to(torch.float64)
+        self.own_box = box.clone()
         if engine.n_points == 0:           # an empty slab can never hold a neighbour
             box[0].fill_(float("inf"))
             box[1].fill_(float("-inf"))
@@ -180,6 +251,41 @@ class SlabTransfer:
         if bad:
             self.cap *= 2
         return not bad
+
+    def _transfer_ghost(self, q, k, radius, want_d2, validate=True):
+        """Owner-only step on the ghost-augmented index + the check that no sample's k-th
+        neighbour ball leaves the ghost zone.  Returns None when the step must be redone with
+        the exchange (only possible with validate=True; otherwise validate() reports it)."""
+        eng = self.engine
+        try:
+            _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True, want_cand=False)
+        except TypeError:            # engines without the want_cand switch (test stand-ins)
+            _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True)
+        if q.shape[0]:
+            kth = out["d2"][:, k - 1]
+            if radius is not None and radius >= 0:
+                kth = torch.clamp(kth, max=float(radius) * float(radius))
+            # a sample must go to the exchange only if its ball reaches another slab's box AND
+            # may stick out of the ghost zone around this slab
+            e = torch.clamp(torch.maximum(self.own_box[0] - q, q - self.own_box[1]), min=0.0)
+            leaves_zone = (torch.sqrt(kth) + torch.sqrt((e * e).sum(dim=1))) * (1.0 + 1e-9) > self.halo
+            ep = torch.clamp(torch.maximum(self.boxes[None, :, 0] - q[:, None, :],
+                                           q[:, None, :] - self.boxes[None, :, 1]), min=0.0)
+            lbp = (ep * ep).sum(dim=2) * (1.0 - 1e-12)              # [m, R]
+            lbp[:, self.rank] = float("inf")
+            reaches_peer = (lbp <= kth[:, None]).any(dim=1)
+            viol = (leaves_zone & reaches_peer).any().to(torch.int32).view(1)
+        else:
+            viol = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        if not want_d2:
+            out.pop("d2")
+        if not validate:
+            if getattr(self, "_flag_acc", None) is None:
+                self._flag_acc = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            torch.maximum(self._flag_acc, viol, out=self._flag_acc)
+            return out
+        dist.all_reduce(viol, op=dist.ReduceOp.MAX, group=self.group)
+        return None if int(viol.item()) else out
 
     def _transfer_fast(self, q, k, radius, want_d2, validate=True):
         """Fixed-capacity exchange on the CUDA engine: route kernel -> all_to_all -> bounded halo
@@ -235,6 +341,12 @@ class SlabTransfer:
         step fully asynchronous; the caller must then call ``validate()`` before trusting it."""
         eng, dev, R = self.engine, self.device, self.world
         m = q.shape[0]
+        if R > 1 and self.halo is not None:
+            out = self._transfer_ghost(q, k, radius, want_d2, validate)
+            if out is not None:
+                self.stats = {"crossing": 0, "sent": 0, "received": 0, "path": "ghost-zone",
+                              "halo": self.halo}
+                return out
         if R > 1 and getattr(eng, "fast", False):
             out = self._transfer_fast(q, k, radius, want_d2, validate)
             if out is not None:

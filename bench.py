@@ -196,9 +196,22 @@ def main():
     q = pkg.synth.samples_device(gu, gv, u0=u0, u1=u1, center=w.center, device=dev)
     m = q.shape[0]
     torch.cuda.synchronize()
-    pkg.DeviceTree(pos, attrs).close()          # warm-up build (module load, allocator)
+    ids = own_box = halo = None
+    n_own = n
+    if world > 1:
+        # slab + ghost zone: the points of the other slabs within `halo` of this slab's box are
+        # exchanged ONCE here, so the steady-state step needs no collective
+        import math
+        rk = math.sqrt(k / (math.pi * (n / (L * L))))       # expected k-th neighbour distance
+        halo = max(6.0 * rk, 2.0 * (w.radius or 0.0))
+        ids = torch.arange(rank * n, (rank + 1) * n, dtype=torch.int32, device=dev)
+        own_box = pkg.dist.points_box(pos)
+        boxes = pkg.dist.gather_boxes(own_box)
+        pos, attrs, ids = pkg.dist.exchange_ghosts(pos, attrs, ids, boxes, halo)
+        n = pos.shape[0]
+    pkg.DeviceTree(pos, attrs, ids).close()     # warm-up build (module load, allocator)
     t0 = time.perf_counter()
-    tree = pkg.DeviceTree(pos, attrs)
+    tree = pkg.DeviceTree(pos, attrs, ids)
     build_wall_ms = (time.perf_counter() - t0) * 1e3
     info = tree.info()
 
@@ -210,7 +223,7 @@ def main():
     slab = None
     if world > 1:
         # slab-sharded: owner k-NN, halo exchange of the boundary samples over NCCL, K5 merge
-        slab = pkg.dist.SlabTransfer(pkg.dist.CudaSlabEngine(tree))
+        slab = pkg.dist.SlabTransfer(pkg.dist.CudaSlabEngine(tree), own_box=own_box, halo=halo)
     result = {}
 
     def step():
@@ -295,7 +308,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w.name, "points_per_gpu": n, "samples_per_gpu": m, "k": k,
+        "config": {"workload": w.name, "points_per_gpu": n_own, "ghost_points_per_gpu": n - n_own,
+                   "samples_per_gpu": m, "k": k,
                    "radius": w.radius, "coord_storage": "f32x4" if info.coord_mode == 1 else "f64",
                    "l2": "flushed between steps (256 MiB write)",
                    "parallelism": f"slab x{world}", "knn_variant": pkg.get_option("knn_variant"),
@@ -312,6 +326,7 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel": "knn_*_kernel",
                      "kernel_ms": ms_per_step},
         "build": {"ms": info.build_ms, "wall_ms": build_wall_ms, "points_per_s": n / (info.build_ms * 1e-3),
+                  "halo": halo,
                   "leaves": int(info.n_leaves), "index_bytes": int(info.device_bytes)},
     }
     if slab is not None:

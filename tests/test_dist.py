@@ -69,8 +69,16 @@ class OracleEngine:
         c = lists.numpy().reshape(r, m, k, 32).view(self.pkg.CAND_DTYPE).reshape(r, m, k)
         c = np.transpose(c, (1, 0, 2)).reshape(m, r * k)
         key_id = np.where(c["id"] < 0, np.iinfo(np.int32).max, c["id"])
-        order = np.lexsort((key_id, c["d2"]), axis=1)[:, :k]
-        sel = np.take_along_axis(c, order, axis=1)
+        order = np.lexsort((key_id, c["d2"]), axis=1)
+        srt = np.take_along_axis(c, order, axis=1)
+        # the same global point may arrive from two ranks (ghost zones): keep the first copy
+        dup = np.zeros(srt.shape, dtype=bool)
+        dup[:, 1:] = (srt["id"][:, 1:] == srt["id"][:, :-1]) & (srt["id"][:, 1:] >= 0)
+        rank_keep = np.argsort(dup, axis=1, kind="stable")[:, :k]
+        sel = np.take_along_axis(srt, rank_keep, axis=1)
+        empty = np.zeros((), dtype=self.pkg.CAND_DTYPE)
+        empty["d2"], empty["id"] = np.inf, -1
+        sel = np.where(np.take_along_axis(dup, rank_keep, axis=1), empty, sel)
         # blend with the oracle's definition on a scratch cloud made of the selected records
         flat = sel.reshape(-1)
         P = self.pkg.make_points(np.zeros((len(flat), 3)),
@@ -107,8 +115,30 @@ def _worker(rank, world, port, case, tmpdir):
             mine = mine[:0]
         x_cut = [-np.inf] + [P["ver"][order[c], 0] for c in cuts[1:-1]] + [np.inf]
         own_q = np.nonzero((V["ver"][:, 0] >= x_cut[rank]) & (V["ver"][:, 0] < x_cut[rank + 1]))[0]
-        eng = OracleEngine(pkg, pto, P[mine], mine)
-        st = pkg.dist.SlabTransfer(eng)
+        halo = case.get("halo")
+        if halo is None:
+            eng = OracleEngine(pkg, pto, P[mine], mine)
+            st = pkg.dist.SlabTransfer(eng)
+        else:
+            # ghost zones: exchange the points near the other slabs once, then owner-only steps
+            sub = P[mine]
+            pos = torch.zeros((len(mine), 4), dtype=torch.float64)
+            pos[:, :3] = torch.from_numpy(sub["ver"].copy())
+            at = np.zeros(len(mine), dtype=pkg.ATTR_DTYPE)
+            at["nx"], at["ny"], at["nz"] = sub["normal"][:, 0], sub["normal"][:, 1], sub["normal"][:, 2]
+            at["rgba"][:, :3] = sub["color"]
+            at["rgba"][:, 3] = 255
+            attrs = torch.from_numpy(at.view(np.uint8).reshape(-1, 16).copy())
+            own_box = pkg.dist.points_box(pos)
+            boxes = pkg.dist.gather_boxes(own_box)
+            gpos, gattr, gids = pkg.dist.exchange_ghosts(pos, attrs, torch.from_numpy(mine.astype(np.int32)),
+                                                         boxes, halo)
+            ga = gattr.numpy().view(pkg.ATTR_DTYPE).reshape(-1)
+            P2 = pkg.make_points(gpos[:, :3].numpy(), normal=np.stack([ga["nx"], ga["ny"], ga["nz"]], 1),
+                                 color=ga["rgba"][:, :3].astype(np.int32))
+            assert np.array_equal(P2["ver"], P["ver"][gids.numpy()])      # ghosts are exact copies
+            eng = OracleEngine(pkg, pto, P2, gids.numpy())
+            st = pkg.dist.SlabTransfer(eng, own_box=own_box, halo=halo)
         out = st.transfer(torch.from_numpy(np.ascontiguousarray(V["ver"][own_q])), k,
                           radius=radius, want_d2=True)
         # reference: one index over the points every rank actually holds
@@ -123,6 +153,8 @@ def _worker(rank, world, port, case, tmpdir):
         assert np.array_equal(out["d2"].numpy(), ref_d2), f"rank {rank}: d2"
         assert np.array_equal(out["rgba"].numpy(), ref_rgba), f"rank {rank}: rgba"
         assert np.allclose(out["normal"].numpy(), ref_nrm, rtol=1e-5, atol=1e-7)
+        if case.get("expect_path"):
+            assert st.stats["path"] == case["expect_path"], st.stats
         stats = torch.tensor([st.stats["crossing"], len(own_q)], dtype=torch.int64)
         dist.all_reduce(stats)
         if rank == 0:
@@ -136,13 +168,20 @@ CASES = {
     "radius_k16": dict(n=40_000, g=40, k=16, radius=0.5),
     "tiny_cloud_k32": dict(n=50, g=10, k=32, radius=None),       # every sample crosses
     "empty_slab": dict(n=20_000, g=30, k=8, radius=None, empty_rank=1),
+    # ghost zone wide enough: owner-only step, no per-step collective
+    "ghost_zone_k8": dict(n=40_000, g=40, k=8, radius=None, halo=3.0, expect_path="ghost-zone"),
+    "ghost_zone_radius": dict(n=40_000, g=40, k=16, radius=0.5, halo=0.8, expect_path="ghost-zone"),
+    # ghost zone too narrow: the step falls back to the exchange, duplicates are dropped
+    "ghost_zone_too_small": dict(n=40_000, g=40, k=8, radius=None, halo=0.05,
+                                 expect_path="exact-size"),
 }
 
 
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_slab_transfer_matches_single_index(case, world, tmp_path):
-    if world == 3 and case not in ("unbounded_k8", "tiny_cloud_k32"):
+    if world == 3 and case not in ("unbounded_k8", "tiny_cloud_k32", "ghost_zone_k8",
+                                   "ghost_zone_too_small"):
         pytest.skip("covered at world_size 2")
     port = 29500 + (os.getpid() * 7 + hash(case) + world) % 2000
     mp.spawn(_worker, args=(world, port, CASES[case], str(tmp_path)), nprocs=world, join=True)

@@ -59,6 +59,30 @@ def _worker(rank, world, port, k, radius):
         for name in ("idx", "d2", "rgba", "normal"):
             assert torch.equal(out[name], out2[name]), name
         tree.close()
+        # ---- slab + ghost zone: points near the other slabs exchanged once at build time, then
+        # owner-only steps with no collective; still bit-identical to the whole-cloud oracle
+        halo = 3.0 if radius is None else radius + 1.0
+        own_box = pkg.dist.points_box(pos)
+        boxes = pkg.dist.gather_boxes(own_box)
+        gpos, gattr, gids = pkg.dist.exchange_ghosts(
+            pos, torch.from_numpy(attrs.view(np.uint8).reshape(-1, 16)).to(dev),
+            torch.from_numpy(mine).to(dev), boxes, halo)
+        assert gpos.shape[0] > pos.shape[0]
+        gtree = pkg.DeviceTree(gpos, gattr, gids)
+        gst = pkg.dist.SlabTransfer(pkg.dist.CudaSlabEngine(gtree), own_box=own_box, halo=halo)
+        gout = gst.transfer(q, k, radius=radius, want_d2=True)
+        torch.cuda.synchronize()
+        assert gst.stats["path"] == "ghost-zone", gst.stats
+        for name in ("idx", "d2", "rgba", "normal"):
+            assert torch.equal(out[name], gout[name]), name
+        # a ghost zone that is too narrow falls back to the exchange (duplicates dropped)
+        gst2 = pkg.dist.SlabTransfer(pkg.dist.CudaSlabEngine(gtree), own_box=own_box, halo=0.01)
+        gout2 = gst2.transfer(q, k, radius=radius, want_d2=True)
+        torch.cuda.synchronize()
+        assert gst2.stats["path"] == "fast", gst2.stats
+        for name in ("idx", "d2", "rgba", "normal"):
+            assert torch.equal(out[name], gout2[name]), name
+        gtree.close()
     finally:
         dist.destroy_process_group()
 
