@@ -295,6 +295,15 @@ int pt_halo_route_device(const double *queries_xyz, const pt_cand *own_cand, siz
                              (cudaStream_t)stream);
 }
 
+int pt_ghost_check_device(const double *queries_xyz, const double *d2, size_t m, int k,
+                          double radius, const double *boxes, int n_ranks, int self, double halo,
+                          uint32_t *flag, void *stream)
+{
+    if ((m && (!queries_xyz || !d2)) || !boxes || !flag || m > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
+    return launch_ghost_check(queries_xyz, d2, (uint32_t)m, k, radius_to_r2(radius), boxes, n_ranks,
+                              self, halo, flag, (cudaStream_t)stream);
+}
+
 int pt_halo_prepare_device(const double *recv, int n_ranks, uint32_t cap, double *queries_out,
                            double *radius2_out, void *stream)
 {

@@ -77,6 +77,9 @@ int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *
                  double *d2_out, uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
                  cudaStream_t s);
 
+int launch_ghost_check(const double *q, const double *d2, uint32_t m, int k, double r2,
+                       const double *boxes, int n_ranks, int self, double halo, uint32_t *flag,
+                       cudaStream_t s);
 int launch_halo_route(const double *q, const pt_cand *own, uint32_t m, int k, double r2,
                       const double *boxes, int n_ranks, int self, uint32_t cap, double *send,
                       int32_t *sel, uint32_t *counts, uint32_t *overflow_flag, cudaStream_t s);

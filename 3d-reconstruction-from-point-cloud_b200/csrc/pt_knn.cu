@@ -561,6 +561,49 @@ halo_merge_kernel(pt_cand *own, const pt_cand *back, const int32_t *sel, const u
                          normal_out ? normal_out + 3 * (size_t)q : nullptr);
 }
 
+// Ghost-zone check: flags the step if some sample's k-th-neighbour ball
+// both reaches another slab's box and may stick out of the ghost zone around this slab.
+__global__ void __launch_bounds__(256)
+ghost_check_kernel(const double *q, const double *d2, uint32_t m, int k, double r2,
+                   const double *boxes, int n_ranks, int self, double halo, uint32_t *flag)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool viol = false;
+    if (s < m) {
+        const double x = q[3 * (size_t)s], y = q[3 * (size_t)s + 1], z = q[3 * (size_t)s + 2];
+        const double bound = fmin(d2[(size_t)s * k + (k - 1)], r2);
+        const double *ob = boxes + 6 * self;
+        const double ox = fmax(fmax(ob[0] - x, x - ob[3]), 0.0);
+        const double oy = fmax(fmax(ob[1] - y, y - ob[4]), 0.0);
+        const double oz = fmax(fmax(ob[2] - z, z - ob[5]), 0.0);
+        const bool leaves = (sqrt(bound) + sqrt(ox * ox + oy * oy + oz * oz)) * (1.0 + 1e-9) > halo;
+        if (leaves) {
+            for (int r = 0; r < n_ranks && !viol; ++r) {
+                if (r == self) continue;
+                const double *b = boxes + 6 * r;
+                const double ex = fmax(fmax(b[0] - x, x - b[3]), 0.0);
+                const double ey = fmax(fmax(b[1] - y, y - b[4]), 0.0);
+                const double ez = fmax(fmax(b[2] - z, z - b[5]), 0.0);
+                const double lb = (ex * ex + ey * ey + ez * ez) * (1.0 - 1e-12);
+                viol = lb <= bound && lb < INFINITY;
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, viol) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+int launch_ghost_check(const double *q, const double *d2, uint32_t m, int k, double r2,
+                       const double *boxes, int n_ranks, int self, double halo, uint32_t *flag,
+                       cudaStream_t s)
+{
+    if (m == 0) return PT_OK;
+    if (k < 1 || k > PT_MAX_K || self < 0 || self >= n_ranks) return PT_ERR_INVALID_ARG;
+    ghost_check_kernel<<<(m + 255) / 256, 256, 0, s>>>(q, d2, m, k, r2, boxes, n_ranks, self, halo, flag);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
 int launch_halo_route(const double *q, const pt_cand *own, uint32_t m, int k, double r2,
                       const double *boxes, int n_ranks, int self, uint32_t cap, double *send,
                       int32_t *sel, uint32_t *counts, uint32_t *overflow_flag, cudaStream_t s)

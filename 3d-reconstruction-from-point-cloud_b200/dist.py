@@ -90,6 +90,14 @@ class CudaSlabEngine:
             self._halo_key = key
         return self._halo
 
+    def ghost_check(self, q, d2, k, radius, boxes6, rank, halo, flag):
+        api = self._api
+        with torch.cuda.device(self.device):
+            api._check(api.lib().pt_ghost_check_device(
+                api._tptr(q), api._tptr(d2), q.shape[0], int(k), api._radius(radius),
+                api._tptr(boxes6), boxes6.shape[0], int(rank), float(halo), api._tptr(flag),
+                api._stream_ptr()), "pt_ghost_check_device")
+
     def halo_route(self, q, own, k, radius, boxes6, rank, cap, h):
         api = self._api
         with torch.cuda.device(self.device):
@@ -261,7 +269,10 @@ class SlabTransfer:
             _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True, want_cand=False)
         except TypeError:            # engines without the want_cand switch (test stand-ins)
             _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True)
-        if q.shape[0]:
+        if q.shape[0] and hasattr(eng, "ghost_check"):       # one small kernel on the CUDA engine
+            viol = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            eng.ghost_check(q, out["d2"], k, radius, self.boxes6, self.rank, self.halo, viol)
+        elif q.shape[0]:
             kth = out["d2"][:, k - 1]
             if radius is not None and radius >= 0:
                 kth = torch.clamp(kth, max=float(radius) * float(radius))

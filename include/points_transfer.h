@@ -170,6 +170,14 @@ int pt_halo_merge_device(pt_cand *own_cand, const pt_cand *back, const int32_t *
                          const uint32_t *count, uint32_t cap, int k, int32_t *idx_out,
                          double *d2_out, uint8_t *rgba_out, float *normal_out, void *stream);
 
+/* Ghost-zone check for slab indexes that also hold the other slabs' points within `halo` of
+ * this slab's box: ORs 1 into *flag if some sample's k-th-neighbour ball (d2[m*k], bounded by
+ * radius) reaches another slab's box and may leave the ghost zone, i.e. the step needs the
+ * exchange after all.  boxes as in pt_halo_route_device (the slabs' OWN boxes). */
+int pt_ghost_check_device(const double *queries_xyz, const double *d2, size_t m, int k,
+                          double radius, const double *boxes, int n_ranks, int self,
+                          double halo, uint32_t *flag, void *stream);
+
 /* Tuning / introspection. */
 int pt_set_option(const char *name, int value); /* e.g. "knn_variant" */
 int pt_get_option(const char *name, int *value);
