@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=-1, help="knn kernel variant (tuning)")
     ap.add_argument("--order", type=int, default=-1, help="0 Morton, 1 Hilbert (tuning)")
     ap.add_argument("--sort", type=int, default=-1, help="1 hand-written radix sort, 0 CUB (tuning)")
+    ap.add_argument("--slab", type=int, default=-1, help="(diagnosis) use the slab of this rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-window", type=float, default=0.25,
                     help="side fraction of the domain used for the bounded CPU sample")
@@ -190,7 +191,8 @@ def main():
 
     w, n, gu, gv, k = resolve_workload(args, pkg)
     L = pkg.synth.L_DOMAIN
-    u0, u1 = rank * L, (rank + 1) * L            # weak scaling: one slab of the scan per rank
+    slab_id = rank if args.slab < 0 else args.slab
+    u0, u1 = slab_id * L, (slab_id + 1) * L      # weak scaling: one slab of the scan per rank
     pos, attrs = pkg.synth.cloud_device(n, w.seed, u0=u0, u1=u1, kind=w.kind, sigma=w.sigma,
                                         first_index=rank * n, device=dev)
     q = pkg.synth.samples_device(gu, gv, u0=u0, u1=u1, center=w.center, device=dev)
@@ -244,11 +246,13 @@ def main():
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     torch.cuda.synchronize()
+    host_t0 = time.perf_counter()
     for a, b in evs:
         flush.zero_()
         a.record()
         step()
         b.record()
+    host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # CPU time to enqueue a step
     torch.cuda.synchronize()
     launches = pkg.kernel_launch_count() - launches0
     if slab is not None and not slab.validate():
@@ -256,7 +260,11 @@ def main():
     clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    ms_per_rank = [dev_ms / args.steps]
     if world > 1:
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        ms_per_rank = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = world * m / (ms_per_step * 1e-3)
@@ -319,7 +327,8 @@ def main():
                 "d2h_bytes_per_step": m * (4 * k + 4 + 12), "ms_per_step": e2e_s * 1e3,
                 "h2d_ms": info2.last_h2d_ms, "kernel_ms": info2.last_query_ms,
                 "d2h_ms": info2.last_d2h_ms},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "ms_per_rank": ms_per_rank,
+        "host_issue_ms_per_step": host_issue_ms,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
