@@ -46,7 +46,7 @@ ABI_SYMBOLS = (
     "pt_version", "pt_status_string", "pt_device_count", "pt_index_build", "pt_index_free",
     "pt_index_get_info", "pt_knn", "pt_transfer", "pt_index_build_device", "pt_query_device",
     "pt_merge_device", "pt_halo_route_device", "pt_halo_prepare_device",
-    "pt_halo_merge_device", "pt_ghost_check_device", "pt_set_option", "pt_get_option", "pt_kernel_launch_count",
+    "pt_halo_merge_device", "pt_ghost_check_device", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
     "pt_synth_cloud_device", "pt_synth_samples_device", "pt_synth_pack_points_device",
     "pt_synth_pack_queries_device",
 )
@@ -154,6 +154,15 @@ def device_count():
 
 def kernel_launch_count():
     return int(lib().pt_kernel_launch_count())
+
+
+def debug_stats(reset=True):
+    """Work counters of the query kernel (zeros unless the library was built with -DPT_STATS)."""
+    buf = (ctypes.c_uint64 * 16)()
+    _check(lib().pt_debug_stats(buf, 1 if reset else 0), "pt_debug_stats")
+    names = ("expansions", "leaves", "pushes", "pops", "compactions", "heap_inserts", "parked",
+             "warp_rounds", "overflowed", "samples", "warp_drain_iters", "warp_expand_iters")
+    return {n: int(buf[i]) for i, n in enumerate(names)}
 
 
 def set_option(name, value):

@@ -42,6 +42,8 @@ int map_cuda_error(cudaError_t e)
 int opt_knn_variant() { return g_knn_variant.load(); }
 int opt_order() { return g_order.load(); }
 int opt_sort() { return g_sort.load(); }
+static std::atomic<int> g_smem_pad{0};   // diagnosis: extra dynamic smem per query block (occupancy probe)
+int opt_smem_pad() { return g_smem_pad.load(); }
 
 int set_option(const char *name, int value)
 {
@@ -49,6 +51,7 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "knn_variant")) { g_knn_variant.store(value); return PT_OK; }
     if (!strcmp(name, "order")) { g_order.store(value); return PT_OK; }
     if (!strcmp(name, "sort")) { g_sort.store(value); return PT_OK; }
+    if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }
     if (!strcmp(name, "verbose")) { g_verbose.store(value ? 1 : 0); return PT_OK; }
     return PT_ERR_INVALID_ARG;
 }
@@ -58,6 +61,7 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "knn_variant")) { *value = g_knn_variant.load(); return PT_OK; }
     if (!strcmp(name, "order")) { *value = g_order.load(); return PT_OK; }
     if (!strcmp(name, "sort")) { *value = g_sort.load(); return PT_OK; }
+    if (!strcmp(name, "smem_pad")) { *value = g_smem_pad.load(); return PT_OK; }
     if (!strcmp(name, "verbose")) { *value = verbose() ? 1 : 0; return PT_OK; }
     return PT_ERR_INVALID_ARG;
 }
@@ -98,6 +102,7 @@ static void destroy_index(pt_index *ix)
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     cudaFree(ix->pts); cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->boxes);
     cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf);
+    cudaFree(ix->ws_fin);
     for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
     for (auto &e : ix->cev) if (e) cudaEventDestroy(e);
     for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);
@@ -156,6 +161,11 @@ int pt_device_count(void)
 uint64_t pt_kernel_launch_count(void) { return g_launches.load(); }
 int pt_set_option(const char *name, int value) { return set_option(name, value); }
 int pt_get_option(const char *name, int *value) { return get_option(name, value); }
+int pt_debug_stats(uint64_t *out16, int reset)
+{
+    if (!out16) return PT_ERR_INVALID_ARG;
+    return debug_stats(reinterpret_cast<unsigned long long *>(out16), reset);
+}
 
 int pt_index_build(const void *points, size_t n, const pt_build_opts *opts, pt_index **out)
 {
@@ -266,7 +276,7 @@ int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, do
     if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
     if ((rgba_out || normal_out) && !ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
     PT_CUDA(cudaSetDevice(ix->device));
-    PT_TRY(ensure_overflow_slots(ix, (uint32_t)m, 1));
+    PT_TRY(ensure_overflow_slots(ix, (uint32_t)m, 1, k));
     return query_device_slot(ix, queries_xyz, m, k, radius, radius2_per_query, idx_out, d2_out,
                              rgba_out, normal_out, cand_out, (cudaStream_t)stream, 0);
 }
@@ -352,7 +362,7 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
         if (!ix->cs[i]) PT_CUDA(cudaStreamCreateWithFlags(&ix->cs[i], cudaStreamNonBlocking));
         if (!ix->cev[i]) PT_CUDA(cudaEventCreateWithFlags(&ix->cev[i], cudaEventDisableTiming));
     }
-    PT_TRY(ensure_overflow_slots(ix, (uint32_t)chunk, n_streams));
+    PT_TRY(ensure_overflow_slots(ix, (uint32_t)chunk, n_streams, k));
 
     PT_CUDA(cudaEventRecord(ix->ev[0], s));
     for (int i = 0; i < n_streams; ++i) PT_CUDA(cudaStreamWaitEvent(ix->cs[i], ix->ev[0], 0));

@@ -543,7 +543,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     uint32_t counts[MAX_PYR_LEVELS];
     for (;;) {
         counts[levels++] = cnt;
-        total += cnt;
+        total += (cnt + 7u) & ~7u;   // every level starts 256-byte aligned: an 8-box group is 2 lines
         if (cnt == 1) break;
         cnt = (cnt + 1) / 2;
     }
@@ -552,7 +552,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     for (int j = 0; j < levels; ++j) {
         ix->pyr.level[j] = lvl;
         ix->pyr.count[j] = counts[j];
-        lvl += counts[j];
+        lvl += (counts[j] + 7u) & ~7u;
     }
     ix->pyr.n_levels = levels;
     leaf_box_kernel<Out><<<cdiv((uint64_t)ix->n_leaves * 32, 256), 256, 0, s>>>(

@@ -27,6 +27,8 @@ struct pt_index {
     void  *ws_out = nullptr;   size_t ws_out_bytes = 0;    // idx | d2 | rgba | normal
     void  *ws_ovf = nullptr;   size_t ws_ovf_bytes = 0;    // queue-overflow count + sample list,
     uint32_t ovf_slot_words = 0;                           //   one slot per concurrent launch
+    void  *ws_fin = nullptr;   size_t ws_fin_bytes = 0;    // stream kernel: unsorted candidate rows
+    size_t fin_slot_bytes = 0;
     cudaStream_t cs[3]{};                                  // chunk streams of the host-buffer API
     cudaEvent_t  cev[3]{};
 };
@@ -71,7 +73,7 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
                       bool *representable);
 int unpack_queries_aos(const void *raw80_dev, size_t m, double *xyz_dev, cudaStream_t s);
 
-int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots);
+int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots, int k);
 int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot = 0);
 int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *idx_out,
                  double *d2_out, uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
@@ -99,5 +101,7 @@ int  set_option(const char *name, int value);
 int  opt_knn_variant();
 int  opt_order();
 int  opt_sort();
+int  opt_smem_pad();
+int  debug_stats(unsigned long long *out16, int reset);
 
 }  // namespace pt

@@ -16,6 +16,17 @@
 
 namespace pt {
 
+// -DPT_STATS: per-launch work counters (diagnosis builds only; pt_debug_stats reads them)
+#ifdef PT_STATS
+__device__ unsigned long long g_stats[16];
+#define PT_STAT(slot, v) (st_[slot] += (v))
+#else
+#define PT_STAT(slot, v) ((void)0)
+#endif
+// slots: 0 expansions, 1 leaves, 2 pushes, 3 pops, 4 compactions, 5 heap inserts, 6 candidates
+// parked, 7 warp rounds, 8 overflowed samples, 9 samples, 10 drain iterations (warp), 11 expand
+// iterations (warp)
+
 #ifndef PT_T_THREADS
 #define PT_T_THREADS 32      // one warp per block: finest scheduling granularity (sweep: 32 > 64 > 128)
 #endif
@@ -93,6 +104,10 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     const float qup[3] = {__double2float_ru(qx), __double2float_ru(qy), __double2float_ru(qz)};
     float bound = __double2float_ru(r2);
 
+#ifdef PT_STATS
+    unsigned st_[16];
+    for (int a = 0; a < 16; ++a) st_[a] = 0;
+#endif
     int hn = 0;                 // candidates held; the column is a max-heap once hn == k
     double root_d = INFINITY;   // heap root (current k-th) -- meaningful once hn == k
     int root_i = IDX_NONE;
@@ -101,7 +116,9 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     // queue entry: key = bound bits with the low 4 mantissa bits replaced by the node's t-level
     // (still a valid, slightly smaller lower bound); word = unvisited-children mask << 23 | id
     auto pq_push = [&](uint32_t key, uint32_t word) {
+        PT_STAT(2, 1);
         if (pq_n == TPQ_CAP) {
+            PT_STAT(4, 1);
             // full: the bound only decreases, so entries above it are dead -- drop them and
             // rebuild the heap (rare); only a queue full of live entries is an overflow
             int live = 0;
@@ -172,12 +189,15 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
                 if (pq_n == 0) { done = true; break; }
                 uint32_t key, word;
                 pq_pop(key, word);
+                PT_STAT(3, 1);
                 if (__uint_as_float(key & ~0xfu) > bound) { done = true; break; }  // rest is farther
                 cur_tl = (int)(key & 0xfu);
                 cur_id = word & 0x7fffffu;
                 cur_mask = word >> 23;
             }
             cur_valid = false;
+            PT_STAT(0, 1);
+            if (tid == (unsigned)(__ffs(__activemask()) - 1)) PT_STAT(11, 1);
             // expand: test the unvisited children (t-level cur_tl - 1)
             const int pl = (cur_tl - 1) * T_LOG;
             const uint32_t cnt = P.pyr.count[pl];
@@ -233,6 +253,8 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         if (__all_sync(0xffffffffu, done)) break;
 
         // ---- leaf phase: every lane that holds a leaf scans it, 8 points per chunk -------------
+        PT_STAT(1, leaf >= 0 ? 1 : 0);
+        if (tid == 0) PT_STAT(7, 1);
         const uint32_t base = (uint32_t)(leaf < 0 ? 0 : leaf) * LEAF;
 #pragma unroll 1
         for (int chunk = 0; chunk < LEAF / PT_T_CHUNK; ++chunk) {
@@ -249,14 +271,17 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
                         pdd[pend * T_THREADS] = d;
                         pdi[pend * T_THREADS] = pidx;
                         ++pend;
+                        PT_STAT(6, 1);
                     }
                 }
             }
             while (__any_sync(0xffffffffu, pend > 0)) {
+                if (tid == 0) PT_STAT(10, 1);
                 if (pend > 0) {
                     --pend;
                     const double d = pdd[pend * T_THREADS];
                     const int pidx = pdi[pend * T_THREADS];
+                    if (hn < k || key_less(d, pidx, root_d, root_i)) PT_STAT(5, 1);
                     if (hn < k) {
                         hd[hn * T_THREADS] = d;
                         hi[hn * T_THREADS] = pidx;
@@ -276,6 +301,15 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         if (hn == k) bound = __double2float_ru(fmin(root_d, r2));
     }
 
+#ifdef PT_STATS
+    st_[8] = overflow ? 1 : 0;
+    st_[9] = q < P.m ? 1 : 0;
+    for (int a = 0; a < 12; ++a) {
+        unsigned v = st_[a];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (tid == 0 && v) atomicAdd(&g_stats[a], (unsigned long long)v);
+    }
+#endif
     if (q >= P.m) return;
     if (overflow) {
         uint32_t slot = atomicAdd(ovf_count, 1u);
@@ -337,13 +371,29 @@ static int launch_thread(const QueryParams &qp, uint32_t *count, uint32_t *list,
     if (!attr_set[which]) {
         PT_CUDA(cudaFuncSetAttribute(knn_thread_kernel<PT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)thread_kernel_smem(PT_MAX_K)));
+                                     200 * 1024));
         attr_set[which] = true;
     }
     unsigned blocks = (qp.m + T_THREADS - 1) / T_THREADS;
-    knn_thread_kernel<PT><<<blocks, T_THREADS, thread_kernel_smem(qp.k), s>>>(qp, count, list);
+    knn_thread_kernel<PT><<<blocks, T_THREADS, thread_kernel_smem(qp.k) + (size_t)opt_smem_pad(), s>>>(qp, count, list);
     count_launch();
     PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int debug_stats(unsigned long long *out16, int reset)
+{
+    for (int a = 0; a < 16; ++a) out16[a] = 0;
+#ifdef PT_STATS
+    PT_CUDA(cudaDeviceSynchronize());
+    PT_CUDA(cudaMemcpyFromSymbol(out16, g_stats, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {};
+        PT_CUDA(cudaMemcpyToSymbol(g_stats, z, sizeof z));
+    }
+#else
+    (void)reset;
+#endif
     return PT_OK;
 }
 

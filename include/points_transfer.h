@@ -181,6 +181,9 @@ int pt_ghost_check_device(const double *queries_xyz, const double *d2, size_t m,
 /* Tuning / introspection. */
 int pt_set_option(const char *name, int value); /* e.g. "knn_variant" */
 int pt_get_option(const char *name, int *value);
+/* Work counters of the query kernel since the last reset (16 words; all zero unless the library
+ * was built with -DPT_STATS, a diagnosis build).  Synchronises the device. */
+int pt_debug_stats(uint64_t *out16, int reset);
 /* Number of kernels this library launched since process start (gpu_launches). */
 uint64_t pt_kernel_launch_count(void);
 
