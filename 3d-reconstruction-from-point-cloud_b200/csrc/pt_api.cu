@@ -102,7 +102,6 @@ static void destroy_index(pt_index *ix)
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     cudaFree(ix->pts); cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->boxes);
     cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf);
-    cudaFree(ix->ws_fin);
     for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
     for (auto &e : ix->cev) if (e) cudaEventDestroy(e);
     for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);

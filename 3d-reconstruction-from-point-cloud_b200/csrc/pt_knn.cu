@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 }  // namespace pt
 #include "pt_knn_octet.cuh"
 #include "pt_knn_thread.cuh"
-#include "pt_knn_stream.cuh"
+#include "pt_knn_fkey.cuh"
 namespace pt {
 
 // Octet (variant 1) / thread (variant 2) kernel, then the warp kernel over the samples whose
@@ -367,13 +367,9 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
         return PT_ERR_INVALID_ARG;   // ensure_overflow_slots() was not called for this launch
     uint32_t *count = (uint32_t *)ix->ws_ovf + (size_t)slot * ix->ovf_slot_words;
     uint32_t *list = count + 4;
-    PT_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(uint32_t), s));   // overflow count, next sample
-    if (variant == 3) {
-        const size_t rows = (size_t)qp.m * qp.k;
-        if ((size_t)(slot + 1) * ix->fin_slot_bytes > ix->ws_fin_bytes || rows * 12 > ix->fin_slot_bytes)
-            return PT_ERR_INVALID_ARG;
-        char *scr = (char *)ix->ws_fin + (size_t)slot * ix->fin_slot_bytes;
-        PT_TRY(launch_stream<PT>(qp, count, list, (double *)scr, (int *)(scr + rows * 8), s));
+    PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
+    if (variant == 4) {
+        PT_TRY(launch_fkey<PT>(qp, count, list, s));
     } else if (variant == 2) {
         PT_TRY(launch_thread<PT>(qp, count, list, s));
     } else {
@@ -389,18 +385,7 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
 // Reallocates (device-synchronising) only when it has to grow.
 int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots, int k)
 {
-    if (opt_knn_variant() == 3) {   // scratch rows of the stream kernel: m x k x (d2 + index)
-        size_t per = (((size_t)m_per_slot * (size_t)k * 12) + 255) & ~(size_t)255;
-        if (per < ix->fin_slot_bytes) per = ix->fin_slot_bytes;
-        if (per * slots > ix->ws_fin_bytes) {
-            if (ix->ws_fin) cudaFree(ix->ws_fin);
-            ix->ws_fin = nullptr;
-            ix->ws_fin_bytes = 0;
-            PT_CUDA(cudaMalloc(&ix->ws_fin, per * slots));
-            ix->ws_fin_bytes = per * slots;
-        }
-        ix->fin_slot_bytes = per;
-    }
+    (void)k;
     uint32_t words = m_per_slot + 4;
     if (words < ix->ovf_slot_words) words = ix->ovf_slot_words;
     size_t need = sizeof(uint32_t) * (size_t)words * slots;

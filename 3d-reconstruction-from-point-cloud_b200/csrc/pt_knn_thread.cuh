@@ -47,32 +47,85 @@ constexpr int T_LOG = 3;
 constexpr int TPQ_CAP = PT_TPQ_CAP;
 constexpr int TPD_CAP = PT_T_CHUNK;
 
-// sift `(cd, ci)` down from `pos` in the max-heap column of size n
-__device__ __forceinline__ void heap_sift(double *hd, int *hi, int pos, int n, double cd, int ci)
+// sift `(cd, ci)` down from `pos` in the max-heap column of size n (element j at [j * STRIDE])
+template <int STRIDE>
+__device__ __forceinline__ void heap_sift_s(double *hd, int *hi, int pos, int n, double cd, int ci)
 {
     for (;;) {
         int c = 2 * pos + 1;
         if (c >= n) break;
-        double xd = hd[c * T_THREADS];
-        int xi = hi[c * T_THREADS];
+        double xd = hd[c * STRIDE];
+        int xi = hi[c * STRIDE];
         if (c + 1 < n) {
-            double yd = hd[(c + 1) * T_THREADS];
-            int yi = hi[(c + 1) * T_THREADS];
+            double yd = hd[(c + 1) * STRIDE];
+            int yi = hi[(c + 1) * STRIDE];
             if (key_less(xd, xi, yd, yi)) { xd = yd; xi = yi; ++c; }
         }
         if (!key_less(cd, ci, xd, xi)) break;
-        hd[pos * T_THREADS] = xd;
-        hi[pos * T_THREADS] = xi;
+        hd[pos * STRIDE] = xd;
+        hi[pos * STRIDE] = xi;
         pos = c;
     }
-    hd[pos * T_THREADS] = cd;
-    hi[pos * T_THREADS] = ci;
+    hd[pos * STRIDE] = cd;
+    hi[pos * STRIDE] = ci;
+}
+
+__device__ __forceinline__ void heap_sift(double *hd, int *hi, int pos, int n, double cd, int ci)
+{
+    heap_sift_s<T_THREADS>(hd, hi, pos, n, cd, ci);
 }
 
 __device__ __forceinline__ void heapify(double *hd, int *hi, int n)
 {
     for (int s = n / 2 - 1; s >= 0; --s)
         heap_sift(hd, hi, s, n, hd[s * T_THREADS], hi[s * T_THREADS]);
+}
+
+// Sorts the hn candidates of a column ascending by (d2, index) and writes every output of the
+// sample: neighbour ids, d2, candidate records, blended colour / normal (frozen definition).
+template <int STRIDE>
+__device__ __forceinline__ void emit_sample(const QueryParams &P, uint32_t q, double *hd, int *hi,
+                                            int hn)
+{
+    const int k = P.k;
+    for (int s = hn / 2 - 1; s >= 0; --s)
+        heap_sift_s<STRIDE>(hd, hi, s, hn, hd[s * STRIDE], hi[s * STRIDE]);
+    for (int n = hn - 1; n > 0; --n) {
+        const double ld = hd[n * STRIDE];
+        const int li = hi[n * STRIDE];
+        hd[n * STRIDE] = hd[0];
+        hi[n * STRIDE] = hi[0];
+        heap_sift_s<STRIDE>(hd, hi, 0, n, ld, li);
+    }
+    const bool want_blend = P.rgba_out || P.normal_out;
+    const bool need_attr = (want_blend || P.cand_out) && P.attrs;
+    const size_t o = (size_t)q * k;
+    const int mode = (hn > 0 && hd[0] == 0.0) ? 1 : 0;
+    BlendAcc acc;
+    acc.reset();
+    for (int j = 0; j < k; ++j) {
+        const bool has = j < hn;
+        const double d = has ? hd[j * STRIDE] : INFINITY;
+        const int li = has ? hi[j * STRIDE] : IDX_NONE;
+        const int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
+        if (P.idx_out) P.idx_out[o + j] = gid;
+        if (P.d2_out) P.d2_out[o + j] = d;
+        AttrRaw at{0.f, 0.f, 0.f, 0u};
+        if (has && need_attr) at = load_attr(P.attrs + li);
+        if (P.cand_out) store_cand(P.cand_out + o + j, d, gid, at);
+        if (has && want_blend) acc.add(blend_weight(mode, d, j), at.rgba, at.nx, at.ny, at.nz);
+    }
+    if (want_blend) {
+        uint8_t *ro = P.rgba_out ? P.rgba_out + 4 * (size_t)q : nullptr;
+        float *no = P.normal_out ? P.normal_out + 3 * (size_t)q : nullptr;
+        if (hn == 0) { store_empty_blend(ro, no); return; }
+        if (!acc.weight_ok()) {   // overflowed weights: nearest neighbour only
+            acc.reset();
+            AttrRaw at = load_attr(P.attrs + hi[0]);
+            acc.add(1.0, at.rgba, at.nx, at.ny, at.nz);
+        }
+        acc.store(ro, no);
+    }
 }
 
 template <typename PT>
@@ -317,45 +370,7 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         return;
     }
 
-    // heap-sort the hn held candidates in place -> ascending (d2, index)
-    if (hn < k) heapify(hd, hi, hn);
-    for (int n = hn - 1; n > 0; --n) {
-        const double ld = hd[n * T_THREADS];
-        const int li = hi[n * T_THREADS];
-        hd[n * T_THREADS] = hd[0];
-        hi[n * T_THREADS] = hi[0];
-        heap_sift(hd, hi, 0, n, ld, li);
-    }
-
-    const bool want_blend = P.rgba_out || P.normal_out;
-    const bool need_attr = (want_blend || P.cand_out) && P.attrs;
-    const size_t o = (size_t)q * k;
-    const int mode = (hn > 0 && hd[0] == 0.0) ? 1 : 0;
-    BlendAcc acc;
-    acc.reset();
-    for (int j = 0; j < k; ++j) {
-        const bool has = j < hn;
-        const double d = has ? hd[j * T_THREADS] : INFINITY;
-        const int li = has ? hi[j * T_THREADS] : IDX_NONE;
-        const int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
-        if (P.idx_out) P.idx_out[o + j] = gid;
-        if (P.d2_out) P.d2_out[o + j] = d;
-        AttrRaw at{0.f, 0.f, 0.f, 0u};
-        if (has && need_attr) at = load_attr(P.attrs + li);
-        if (P.cand_out) store_cand(P.cand_out + o + j, d, gid, at);
-        if (has && want_blend) acc.add(blend_weight(mode, d, j), at.rgba, at.nx, at.ny, at.nz);
-    }
-    if (want_blend) {
-        uint8_t *ro = P.rgba_out ? P.rgba_out + 4 * (size_t)q : nullptr;
-        float *no = P.normal_out ? P.normal_out + 3 * (size_t)q : nullptr;
-        if (hn == 0) { store_empty_blend(ro, no); return; }
-        if (!acc.weight_ok()) {   // overflowed weights: nearest neighbour only
-            acc.reset();
-            AttrRaw at = load_attr(P.attrs + hi[0]);
-            acc.add(1.0, at.rgba, at.nx, at.ny, at.nz);
-        }
-        acc.store(ro, no);
-    }
+    emit_sample<T_THREADS>(P, q, hd, hi, hn);   // sort ascending (d2, index), outputs, blend
 }
 
 static inline size_t thread_kernel_smem(int k)

@@ -1,4 +1,4 @@
-"""Variant 3 (stream kernel) against variant 2 on cfg2: bit-equality of every output, timing,
+"""Two kernel variants against each other on a workload (default 2 vs 4 on cfg2): bit-equality of every output, timing,
 and (with a -DPT_STATS build) the work counters."""
 import sys; sys.path.insert(0, "/root/repo")
 import torch, __graft_entry__ as ge
@@ -11,7 +11,8 @@ q = pkg.synth.samples_device(w.gu, w.gv, center=w.center); m = q.shape[0]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 tree = pkg.DeviceTree(pos, attrs)
 res = {}
-for variant in (2, 3):
+variants = [int(a) for a in sys.argv[2:]] or [2, 4]
+for variant in variants:
     pkg.set_option("knn_variant", variant)
     idx = torch.full((m, k), -7, dtype=torch.int32, device=dev); rgba = torch.zeros((m, 4), dtype=torch.uint8, device=dev)
     nrm = torch.zeros((m, 3), dtype=torch.float32, device=dev); d2 = torch.zeros((m, k), dtype=torch.float64, device=dev)
@@ -26,7 +27,7 @@ for variant in (2, 3):
     st = pkg.api.debug_stats()
     per = {kk: round(v / 13 / m, 3) for kk, v in st.items()} if st["samples"] else {}
     print(f"{cfg} variant {variant}: {sum(ts)/len(ts):.4f} ms (min {min(ts):.4f})  m={m} k={k} {per}", flush=True)
-a, b = res[2], res[3]
+a, b = res[variants[0]], res[variants[-1]]
 for name, x, y in zip(("idx", "d2", "rgba", "normal"), a, b):
     same = bool(torch.equal(x, y))
     print(f"  {name}: {'identical' if same else 'DIFFERENT: %d rows' % int((x != y).reshape(m, -1).any(dim=1).sum())}")
