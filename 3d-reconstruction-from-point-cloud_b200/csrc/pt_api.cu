@@ -275,7 +275,7 @@ int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, do
     if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
     if ((rgba_out || normal_out) && !ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
     PT_CUDA(cudaSetDevice(ix->device));
-    PT_TRY(ensure_overflow_slots(ix, (uint32_t)m, 1, k));
+    PT_TRY(ensure_overflow_slots(ix, (uint32_t)m, 1));
     return query_device_slot(ix, queries_xyz, m, k, radius, radius2_per_query, idx_out, d2_out,
                              rgba_out, normal_out, cand_out, (cudaStream_t)stream, 0);
 }
@@ -361,7 +361,7 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
         if (!ix->cs[i]) PT_CUDA(cudaStreamCreateWithFlags(&ix->cs[i], cudaStreamNonBlocking));
         if (!ix->cev[i]) PT_CUDA(cudaEventCreateWithFlags(&ix->cev[i], cudaEventDisableTiming));
     }
-    PT_TRY(ensure_overflow_slots(ix, (uint32_t)chunk, n_streams, k));
+    PT_TRY(ensure_overflow_slots(ix, (uint32_t)chunk, n_streams));
 
     PT_CUDA(cudaEventRecord(ix->ev[0], s));
     for (int i = 0; i < n_streams; ++i) PT_CUDA(cudaStreamWaitEvent(ix->cs[i], ix->ev[0], 0));

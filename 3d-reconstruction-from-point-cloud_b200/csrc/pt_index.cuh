@@ -71,7 +71,7 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
                       bool *representable);
 int unpack_queries_aos(const void *raw80_dev, size_t m, double *xyz_dev, cudaStream_t s);
 
-int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots, int k);
+int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots);
 int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot = 0);
 int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *idx_out,
                  double *d2_out, uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,

@@ -383,9 +383,8 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
 
 // Sizes the overflow workspace for `slots` concurrent launches of up to m_per_slot samples.
 // Reallocates (device-synchronising) only when it has to grow.
-int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots, int k)
+int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots)
 {
-    (void)k;
     uint32_t words = m_per_slot + 4;
     if (words < ix->ovf_slot_words) words = ix->ovf_slot_words;
     size_t need = sizeof(uint32_t) * (size_t)words * slots;

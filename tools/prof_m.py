@@ -3,11 +3,12 @@ import sys; sys.path.insert(0, "/root/repo")
 import torch, __graft_entry__ as ge
 pkg = ge.package(); torch.cuda.set_device(0); dev = torch.device("cuda", 0)
 variants = [int(a) for a in sys.argv[1:]] or [2, 4]
+GRIDS = (448, 896)
 w = pkg.synth.CONFIGS["cfg2"]; k = w.k
 pos, attrs = pkg.synth.cloud_device(w.n_points, w.seed)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 tree = pkg.DeviceTree(pos, attrs)
-for g in (224, 317, 448, 634, 896, 1344):
+for g in GRIDS:
     q = pkg.synth.samples_device(g, g); m = q.shape[0]
     idx = torch.empty((m, k), dtype=torch.int32, device=dev); rgba = torch.empty((m, 4), dtype=torch.uint8, device=dev)
     nrm = torch.empty((m, 3), dtype=torch.float32, device=dev)
