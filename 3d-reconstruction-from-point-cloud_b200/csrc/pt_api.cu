@@ -42,6 +42,8 @@ int map_cuda_error(cudaError_t e)
 int opt_knn_variant() { return g_knn_variant.load(); }
 int opt_order() { return g_order.load(); }
 int opt_sort() { return g_sort.load(); }
+static std::atomic<int> g_host_chunks{3};   // host-buffer API: pipeline chunks per call (3 streams)
+int opt_host_chunks() { return g_host_chunks.load(); }
 static std::atomic<int> g_smem_pad{0};   // diagnosis: extra dynamic smem per query block (occupancy probe)
 int opt_smem_pad() { return g_smem_pad.load(); }
 
@@ -52,6 +54,7 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "order")) { g_order.store(value); return PT_OK; }
     if (!strcmp(name, "sort")) { g_sort.store(value); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }
+    if (!strcmp(name, "host_chunks")) { g_host_chunks.store(value < 1 ? 1 : (value > 64 ? 64 : value)); return PT_OK; }
     if (!strcmp(name, "verbose")) { g_verbose.store(value ? 1 : 0); return PT_OK; }
     return PT_ERR_INVALID_ARG;
 }
@@ -62,6 +65,7 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "order")) { *value = g_order.load(); return PT_OK; }
     if (!strcmp(name, "sort")) { *value = g_sort.load(); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { *value = g_smem_pad.load(); return PT_OK; }
+    if (!strcmp(name, "host_chunks")) { *value = g_host_chunks.load(); return PT_OK; }
     if (!strcmp(name, "verbose")) { *value = verbose() ? 1 : 0; return PT_OK; }
     return PT_ERR_INVALID_ARG;
 }
@@ -354,7 +358,8 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
 
     constexpr int NCS = 3;
     size_t chunk = m;
-    if (m >= 32768) chunk = (((m + 3) / 4) + 31) & ~(size_t)31;
+    const size_t want = (size_t)opt_host_chunks();
+    if (m >= 32768 && want > 1) chunk = (((m + want - 1) / want) + 31) & ~(size_t)31;
     const int n_chunks = (int)((m + chunk - 1) / chunk);
     const int n_streams = n_chunks < NCS ? n_chunks : NCS;
     for (int i = 0; i < n_streams; ++i) {

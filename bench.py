@@ -57,6 +57,12 @@ def algorithmic_bytes_per_sample(k):
     return 32 + 36 * k
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the query kernel from the
+# `ncu --set full` capture committed under profiles/ (r1_knn_thread_kernel_ncu_summary.txt):
+# valid only for the workload / kernel it was captured on.
+NCU_TRAFFIC = {("cfg2", 16, 2): 783.25e6 + 17.63e6}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -331,7 +337,11 @@ def main():
         "host_issue_ms_per_step": host_issue_ms,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": (NCU_TRAFFIC.get((args.workload, k, pkg.get_option("knn_variant")))
+                                 if world == 1 and not (args.points or args.grid) else None),
+                     "traffic_source": "ncu --set full, profiles/r1_knn_thread_kernel_ncu_summary.txt",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel": "knn_*_kernel",
                      "kernel_ms": ms_per_step},
         "build": {"ms": info.build_ms, "wall_ms": build_wall_ms, "points_per_s": n / (info.build_ms * 1e-3),
