@@ -170,6 +170,10 @@ def run_cpu_leg(pkg, pto, P, Q, k, radius, steps, warmup):
 # ---------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm must use all the
+        # host cores it can (rank 0 runs alone), so set it before any OpenMP runtime loads
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
