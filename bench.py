@@ -75,12 +75,48 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled
+    from a thread every ~0.5 ms (the region is tens of milliseconds, too short for nvidia-smi's
+    loop mode, which is only the fallback)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x4, "sw_power_cap"))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, pci_bus_id=None):
+        self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+        self.stop_flag, self.thread, self.proc, self.rows = False, None, None, []
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if pci_bus_id:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode())
+                except Exception:
+                    h = None
+            self.handle = h or pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(int(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(h))
+            except Exception:
+                pass
+            time.sleep(0.0005)
 
     def start(self):
+        if self.nvml:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -98,6 +134,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(name for bit, name in self.REASONS if self.mask & bit),
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -112,7 +155,7 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4)
                           if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def resolve_workload(args, pkg):
@@ -250,7 +293,12 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        bus = None
+    sampler = ClockSampler(local_rank, bus)
     sampler.start()
     launches0 = pkg.kernel_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -319,6 +367,9 @@ def main():
     ref_idx = idx if slab is None else result["idx"]
     assert bool((out_idx.to(dev) == ref_idx).all()), "host-buffer and device-buffer paths disagree"
 
+    variant_used = pkg.get_option("knn_variant")
+    if variant_used < 0:      # auto rule of launch_query (pt_knn.cu)
+        variant_used = 4 if (k > 16 or m >= 320000) else 2
     peak, peak_src = measured_peaks()
     alg_bytes = algorithmic_bytes_per_sample(k) * m
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
@@ -330,7 +381,7 @@ def main():
                    "samples_per_gpu": m, "k": k,
                    "radius": w.radius, "coord_storage": "f32x4" if info.coord_mode == 1 else "f64",
                    "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": f"slab x{world}", "knn_variant": pkg.get_option("knn_variant"),
+                   "parallelism": f"slab x{world}", "knn_variant": variant_used,
                    "order": pkg.get_option("order")},
         "e2e": {"value": world * m / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": m * (80 if slab is None else 24),
@@ -342,7 +393,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     "traffic": (NCU_TRAFFIC.get((args.workload, k, pkg.get_option("knn_variant")))
+                     "traffic": (NCU_TRAFFIC.get((args.workload, k, variant_used))
                                  if world == 1 and not (args.points or args.grid) else None),
                      "traffic_source": "ncu --set full, profiles/r1_knn_thread_kernel_ncu_summary.txt",
                      "peak_source": peak_src,

@@ -48,6 +48,7 @@ def test_status_strings_and_options(pkg):
     assert "no CPU fallback" in pkg.status_string(3)
     pkg.set_option("knn_variant", 0)
     assert pkg.get_option("knn_variant") == 0
+    pkg.set_option("knn_variant", -1)                           # back to auto (the default)
     with pytest.raises(pkg.PointsTransferError):
         pkg.set_option("no_such_option", 1)
 

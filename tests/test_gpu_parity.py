@@ -33,7 +33,7 @@ def _check_blend(got_rgba, got_nrm, ref_rgba, ref_nrm):
 @pytest.fixture(autouse=True)
 def _default_options(pkg):
     yield
-    pkg.set_option("knn_variant", 2)
+    pkg.set_option("knn_variant", -1)     # auto (the default)
     pkg.set_option("order", 2)
 
 
