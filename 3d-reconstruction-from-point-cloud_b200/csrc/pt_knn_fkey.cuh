@@ -9,9 +9,9 @@
 // agree to 2^-23 relative, or true ties); it is detected -- a candidate whose key equals the
 // root's, or a root whose key equals one of its children's (in a max-heap a second entry with
 // the root's key always has an ancestor chain of that key, i.e. a tied child of the root) --
-// and the sample is handed to the exact (d2, index) warp kernel through the existing fallback
-// list.  At the end the k winners' exact d2 and index are re-read from the sorted cloud and
-// sorted by (d2, index) as before, so every output is bit-identical to variant 2.
+// and decided on the exact (d2, index) re-read from the sorted cloud.  At the end the k
+// winners' exact d2 and index are re-read as well and sorted by (d2, index) as before, so
+// every output is bit-identical to variant 2.
 // Gains: one 64-bit shared-memory access and one integer compare per heap level instead of
 // two accesses and a three-instruction key compare, and 96 bytes less state per sample
 // (k = 16), i.e. 17 instead of 14 resident warps per SM.
@@ -146,23 +146,31 @@ knn_fkey_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         d = dist2_exact(qx, qy, qz, px, py, pz);
     };
     // after the root changed: its key, and the tie check that keeps every later decision exact.
-    // One tied child is resolved on the exact keys (the larger of the two becomes the root);
-    // three or more entries with the k-th key send the sample to the exact warp kernel.
+    // A second entry with the root's key always shows up as a tied child of the root (its
+    // ancestors all carry that key); then every entry with that key is compared on the exact
+    // (d2, index) and the largest becomes the root -- entries with equal keys can swap places
+    // without breaking the heap.
     auto root_changed = [&]() {
         root_key = e_key(he[0]);
         const bool t1 = k > 1 && e_key(he[1 * T_THREADS]) == root_key;
         const bool t2 = k > 2 && e_key(he[2 * T_THREADS]) == root_key;
         if (!(t1 || t2)) return;
-        if (t1 && t2) { overflow = true; return; }
-        const int c = t1 ? 1 : 2;
-        if ((2 * c + 1 < k && e_key(he[(2 * c + 1) * T_THREADS]) == root_key) ||
-            (2 * c + 2 < k && e_key(he[(2 * c + 2) * T_THREADS]) == root_key)) { overflow = true; return; }
-        const unsigned long long er = he[0], ec = he[c * T_THREADS];
-        double rd, cd;
-        int ri, ci;
-        exact_of(er, rd, ri);
-        exact_of(ec, cd, ci);
-        if (key_less(rd, ri, cd, ci)) { he[0] = ec; he[c * T_THREADS] = er; }
+        double rd;
+        int ri;
+        exact_of(he[0], rd, ri);
+        for (int j = 1; j < k; ++j) {
+            const unsigned long long ej = he[j * T_THREADS];
+            if (e_key(ej) != root_key) continue;
+            double cd;
+            int ci;
+            exact_of(ej, cd, ci);
+            if (key_less(rd, ri, cd, ci)) {
+                he[j * T_THREADS] = he[0];
+                he[0] = ej;
+                rd = cd;
+                ri = ci;
+            }
+        }
     };
 
     bool cur_valid = !done;
