@@ -104,7 +104,17 @@ static void destroy_index(pt_index *ix)
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    cudaFree(ix->pts); cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->boxes);
+    // sorted points and boxes come from the stream-ordered pool (pt_build.cu): back to it
+    if (ix->pts) cudaFreeAsync(ix->pts, ix->stream);
+    if (ix->boxes) cudaFreeAsync(ix->boxes, ix->stream);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    {   // at most 2 GiB stay cached for the next build
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ix->device) == cudaSuccess)
+            cudaMemPoolTrimTo(pool, (size_t)2 << 30);
+        cudaGetLastError();
+    }
+    cudaFree(ix->attrs); cudaFree(ix->ids);
     cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf);
     for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
     for (auto &e : ix->cev) if (e) cudaEventDestroy(e);

@@ -449,6 +449,27 @@ static int sort_pairs(unsigned long long *&keys, unsigned long long *keys_alt, u
 
 static inline unsigned int cdiv(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
 
+// Build temporaries (sort keys / values / counters: ~24 bytes per point) come from the device's
+// stream-ordered memory pool with an unlimited release threshold, so a rebuild reuses them
+// instead of paying cudaMalloc / cudaFree (3-30 ms per GB, host-synchronous) every time.
+static int temp_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    static bool pool_set[64] = {};
+    int dev = 0;
+    PT_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        pool_set[dev] = true;
+    }
+    PT_CUDA(cudaMallocAsync(p, bytes, s));
+    return PT_OK;
+}
+
 template <typename In, typename Out>
 static int build_impl(pt_index *ix, In in, uint32_t n)
 {
@@ -474,7 +495,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
 
     // K1: bbox
     BBoxAcc *acc = nullptr, h_acc;
-    PT_CUDA(cudaMalloc(&acc, sizeof(BBoxAcc)));
+    PT_TRY(temp_alloc((void **)&acc, sizeof(BBoxAcc), s));
     for (int a = 0; a < 3; ++a) { h_acc.lo[a] = ~0ull; h_acc.hi[a] = 0ull; }
     h_acc.non_finite = 0; h_acc.pad = 0;
     PT_CUDA(cudaMemcpyAsync(acc, &h_acc, sizeof h_acc, cudaMemcpyHostToDevice, s));
@@ -486,7 +507,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     }
     PT_CUDA(cudaMemcpyAsync(&h_acc, acc, sizeof h_acc, cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaStreamSynchronize(s));
-    cudaFree(acc);
+    cudaFreeAsync(acc, s);
     if (h_acc.non_finite) return PT_ERR_NON_FINITE;
     KeyParams kp;
     double ext = 0;
@@ -508,7 +529,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     const size_t kbytes = (sizeof(unsigned long long) * (size_t)n + 255) & ~(size_t)255;
     const size_t vbytes = (sizeof(uint32_t) * (size_t)n + 255) & ~(size_t)255;
     char *arena = nullptr;
-    PT_CUDA(cudaMalloc(&arena, 2 * kbytes + 2 * vbytes + radix_sort_workspace_bytes(n)));
+    PT_TRY(temp_alloc((void **)&arena, 2 * kbytes + 2 * vbytes + radix_sort_workspace_bytes(n), s));
     keys = (unsigned long long *)arena;
     keys_alt = (unsigned long long *)(arena + kbytes);
     vals = (uint32_t *)(arena + 2 * kbytes);
@@ -521,14 +542,14 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     int rc = sort_pairs(keys, keys_alt, vals, vals_alt, n, sort_ws, s);
     lap("sort");
     if (rc != PT_OK) {
-        cudaFree(arena);
+        cudaFreeAsync(arena, s);
         return rc;
     }
 
     // gather into leaves
     size_t n_pad = (size_t)ix->n_leaves * LEAF;
     Out *pts = nullptr;
-    PT_CUDA(cudaMalloc(&pts, sizeof(Out) * n_pad));
+    PT_TRY(temp_alloc((void **)&pts, sizeof(Out) * n_pad, s));   // pooled: a rebuild reuses the block
     gather_kernel<In, Out><<<cdiv(n_pad, 256), 256, 0, s>>>(in, vals, n, (uint32_t)n_pad, pts);
     count_launch();
     ix->pts = pts;
@@ -547,7 +568,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
         if (cnt == 1) break;
         cnt = (cnt + 1) / 2;
     }
-    PT_CUDA(cudaMalloc(&ix->boxes, sizeof(Box) * total));
+    PT_TRY(temp_alloc((void **)&ix->boxes, sizeof(Box) * total, s));
     Box *lvl = ix->boxes;
     for (int j = 0; j < levels; ++j) {
         ix->pyr.level[j] = lvl;
@@ -574,7 +595,16 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     PT_CUDA(cudaStreamSynchronize(s));
     lap("boxes");
     PT_CUDA(cudaEventElapsedTime(&ix->build_ms, ix->ev[0], ix->ev[1]));
-    cudaFree(arena);
+    cudaFreeAsync(arena, s);
+    {   // keep at most 2 GiB of temporaries cached for the next build; the rest goes back
+        cudaMemPool_t pool;
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            cudaStreamSynchronize(s);
+            cudaMemPoolTrimTo(pool, (size_t)2 << 30);
+        }
+        cudaGetLastError();
+    }
     ix->device_bytes = sizeof(Out) * n_pad + sizeof(Box) * total +
                        (ix->attrs ? sizeof(pt_attr) * (size_t)n : 0) +
                        (ix->ids ? sizeof(int32_t) * (size_t)n : 0);

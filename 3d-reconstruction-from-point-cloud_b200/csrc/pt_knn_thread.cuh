@@ -83,11 +83,24 @@ __device__ __forceinline__ void heapify(double *hd, int *hi, int n)
 
 // Sorts the hn candidates of a column ascending by (d2, index) and writes every output of the
 // sample: neighbour ids, d2, candidate records, blended colour / normal (frozen definition).
+#ifndef PT_EMIT_PREFETCH
+#define PT_EMIT_PREFETCH 1
+#endif
 template <int STRIDE>
 __device__ __forceinline__ void emit_sample(const QueryParams &P, uint32_t q, double *hd, int *hi,
                                             int hn)
 {
     const int k = P.k;
+#if PT_EMIT_PREFETCH
+    // the winners' attribute records (and ids) are random 16 / 4-byte gathers: pull them into
+    // L2 now, the sort below hides the DRAM latency
+    if ((P.rgba_out || P.normal_out || P.cand_out) && P.attrs)
+        for (int j = 0; j < hn; ++j)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.attrs + hi[j * STRIDE]));
+    if (P.ids)
+        for (int j = 0; j < hn; ++j)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.ids + hi[j * STRIDE]));
+#endif
     for (int s = hn / 2 - 1; s >= 0; --s)
         heap_sift_s<STRIDE>(hd, hi, s, hn, hd[s * STRIDE], hi[s * STRIDE]);
     for (int n = hn - 1; n > 0; --n) {

@@ -5,9 +5,10 @@
 //   rs_hist_kernel    per-tile digit histogram (warp-aggregated shared-memory atomics)
 //                     -> counts[digit][tile]
 //   rs_scan_kernel    per digit, exclusive prefix over the tiles (block scan + carry), digit totals
-//   rs_scatter_kernel stable in-tile ranking with __match_any_sync (a warp walks its 512 keys in
-//                     RS_ROUNDS coalesced rounds; ranks = digit base + tile prefix + preceding warps of
-//                     the tile + preceding rounds + lower lanes with the same digit), scatter
+//   rs_scatter_kernel stable in-tile ranking with __match_any_sync (a warp walks its keys in
+//                     RS_ROUNDS coalesced rounds; tile-local rank = digit start in the tile +
+//                     preceding warps + preceding rounds + lower lanes with the same digit), the
+//                     tile is staged in digit order in shared memory and written out as runs
 // Bytes moved per pass: 8 (hist read) + 12 (scatter read) + 12 (scatter write) per pair.
 // HBM-bound by design; cub::DeviceRadixSort (CCCL, one-sweep) is the number it is compared
 // against in profiles/ (pt_set_option("sort", 0) selects the library call for that comparison).
@@ -97,13 +98,18 @@ rs_scatter_kernel(const unsigned long long *keys_in, const uint32_t *vals_in,
                   unsigned long long *keys_out, uint32_t *vals_out, uint32_t n, int shift,
                   uint32_t num_tiles, const uint32_t *counts, const uint32_t *bases)
 {
-    __shared__ uint32_t whist[RS_WARPS][RS_RADIX];   // per-warp digit counts, then running offsets
+    __shared__ uint32_t whist[RS_WARPS][RS_RADIX];   // per-warp digit counts, then running tile-local offsets
+    __shared__ uint32_t gofs[RS_RADIX];              // digit d: global position of tile-local rank 0 of d, minus that rank
+    __shared__ uint32_t wsum[RS_WARPS];
+    __shared__ unsigned long long skey[RS_TILE];     // the tile in digit order (stable)
+    __shared__ uint32_t sval[RS_TILE];
     const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     for (int j = tid; j < RS_WARPS * RS_RADIX; j += RS_THREADS) (&whist[0][0])[j] = 0;
     __syncthreads();
-    // warp w owns keys [w*512, w*512+512) of the tile, 16 coalesced rounds of 32
-    const uint32_t wbase = blockIdx.x * (uint32_t)RS_TILE + w * (32 * RS_ROUNDS);
+    // warp w owns keys [w*32*ROUNDS, (w+1)*32*ROUNDS) of the tile, ROUNDS coalesced rounds of 32
+    const uint32_t tile0 = blockIdx.x * (uint32_t)RS_TILE;
+    const uint32_t wbase = tile0 + w * (32 * RS_ROUNDS);
     unsigned long long key[RS_ROUNDS];
     uint32_t val[RS_ROUNDS];
 #pragma unroll
@@ -123,10 +129,27 @@ rs_scatter_kernel(const unsigned long long *keys_in, const uint32_t *vals_in,
         __syncwarp();
     }
     __syncthreads();
-    // 2. digit d: global base + this tile's prefix + the preceding warps of the tile
+    // 2. digit d = tid: tile-local start of the digit (exclusive scan of the tile's digit
+    //    totals), per-warp running offsets inside the tile, and the global offset of the run
     {
         const unsigned d = tid;
-        uint32_t off = bases[d] + counts[(size_t)d * num_tiles + blockIdx.x];
+        uint32_t tot = 0;
+#pragma unroll
+        for (int j = 0; j < RS_WARPS; ++j) tot += whist[j][d];
+        uint32_t x = tot;                                  // inclusive scan over the 256 digits
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, s2);
+            if (lane >= (unsigned)s2) x += y;
+        }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        uint32_t pre = 0;
+#pragma unroll
+        for (int j = 0; j < RS_WARPS; ++j) pre += j < (int)w ? wsum[j] : 0;
+        const uint32_t local_start = pre + x - tot;
+        gofs[d] = bases[d] + counts[(size_t)d * num_tiles + blockIdx.x] - local_start;
+        uint32_t off = local_start;
 #pragma unroll
         for (int j = 0; j < RS_WARPS; ++j) {
             const uint32_t c = whist[j][d];
@@ -135,22 +158,35 @@ rs_scatter_kernel(const unsigned long long *keys_in, const uint32_t *vals_in,
         }
     }
     __syncthreads();
-    // 3. stable ranks and scatter
+    // 3. stable tile-local ranks; stage the tile in digit order in shared memory
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
         const bool valid = i < n;
         const unsigned d = valid ? (unsigned)((key[r] >> shift) & 0xffu) : 0x100u;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
-        uint32_t pos = 0;
         if (valid) {
-            pos = whist[w][d] + (uint32_t)__popc(peers & lt);
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            const uint32_t rank = whist[w][d] + (uint32_t)__popc(peers & lt);
+            skey[rank] = key[r];
+            sval[rank] = val[r];
         }
         __syncwarp();
         if (valid && lane == (unsigned)(__ffs(peers) - 1)) whist[w][d] += (uint32_t)__popc(peers);
         __syncwarp();
+    }
+    __syncthreads();
+    // 4. write out: consecutive threads hold consecutive ranks, i.e. runs of one digit that go
+    //    to consecutive global positions -- coalesced stores instead of one sector per pair
+    const uint32_t cnt = min((uint32_t)RS_TILE, n - tile0);
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const uint32_t j = r * RS_THREADS + tid;
+        if (j < cnt) {
+            const unsigned long long kj = skey[j];
+            const uint32_t pos = gofs[(unsigned)((kj >> shift) & 0xffu)] + j;
+            keys_out[pos] = kj;
+            vals_out[pos] = sval[j];
+        }
     }
 }
 
