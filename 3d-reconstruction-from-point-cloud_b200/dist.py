@@ -270,6 +270,16 @@ class SlabTransfer:
         except TypeError:            # engines without the want_cand switch (test stand-ins)
             _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True)
         if q.shape[0] and hasattr(eng, "ghost_check"):       # one small kernel on the CUDA engine
+            if not validate:
+                # deferred check: the kernel ORs (atomically, so chunks on several streams may
+                # share it) straight into the accumulated flag that validate() reduces
+                if getattr(self, "_flag_acc", None) is None:
+                    self._flag_acc = torch.zeros((1,), dtype=torch.int32, device=self.device)
+                eng.ghost_check(q, out["d2"], k, radius, self.boxes6, self.rank, self.halo,
+                                self._flag_acc)
+                if not want_d2:
+                    out.pop("d2")
+                return out
             viol = torch.zeros((1,), dtype=torch.int32, device=self.device)
             eng.ghost_check(q, out["d2"], k, radius, self.boxes6, self.rank, self.halo, viol)
         elif q.shape[0]:
@@ -344,6 +354,48 @@ class SlabTransfer:
         dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=recv_counts,
                                input_split_sizes=list(send_counts), group=self.group)
         return recv, recv_counts
+
+    def transfer_host(self, q_host, k, out, radius=None, chunks=3):
+        """Host-buffer entry point of the sharded path: ``q_host`` float64 [m,3] (pinned for true
+        overlap) holds the samples this rank owns, ``out`` maps "idx" [m,k] int32, "rgba" [m,4]
+        uint8, "normal" [m,3] float32 to (pinned) host tensors that receive the results.  The
+        batch is cut into ``chunks`` pieces pipelined over CUDA streams -- H2D of the samples,
+        the owner step (no collective in the ghost-zone steady state) and the D2H of the results
+        overlap -- with ONE deferred validation (one tiny all-reduce) at the end; if that fails
+        the batch is redone through the exchange path.  Returns after everything has landed."""
+        m = q_host.shape[0]
+        dev = self.device
+        if self.world == 1 or self.halo is None or not getattr(self.engine, "fast", False) or m == 0:
+            r = self.transfer(q_host.to(dev, non_blocking=True), k, radius=radius)
+            for name in ("idx", "rgba", "normal"):
+                out[name].copy_(r[name], non_blocking=True)
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            return
+        chunks = max(1, min(int(chunks), m))
+        step = -(-m // chunks)
+        if getattr(self, "_host_streams", None) is None:
+            self._host_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        cur = torch.cuda.current_stream(dev)
+        keep = []
+        for c in range(chunks):
+            lo, hi = c * step, min(m, (c + 1) * step)
+            st = self._host_streams[c % len(self._host_streams)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                qd = q_host[lo:hi].to(dev, non_blocking=True)
+                r = self.transfer(qd, k, radius=radius, validate=False)
+                for name in ("idx", "rgba", "normal"):
+                    out[name][lo:hi].copy_(r[name], non_blocking=True)
+                keep.append((qd, r))
+        for st in self._host_streams:
+            cur.wait_stream(st)
+        torch.cuda.synchronize(dev)
+        if not self.validate():            # some sample needed the exchange: exact path, whole batch
+            r = self.transfer(q_host.to(dev, non_blocking=True), k, radius=radius)
+            for name in ("idx", "rgba", "normal"):
+                out[name].copy_(r[name], non_blocking=True)
+            torch.cuda.synchronize(dev)
 
     def transfer(self, q, k, radius=None, want_d2=False, validate=True):
         """q float64 [m,3] on the engine's device (samples owned by this rank).

@@ -341,14 +341,10 @@ def main():
         if slab is None:
             tree.transfer(qh_np, k, radius=w.radius, out=out)      # pt_transfer: host in, host out
         else:
-            # multi-GPU public API: pinned host samples -> device, collective transfer, results
-            # back to pinned host memory
-            qd = q_xyz_host.to(dev, non_blocking=True)
-            r = slab.transfer(qd, k, radius=w.radius)
-            out_idx.copy_(r["idx"], non_blocking=True)
-            out_rgba.copy_(r["rgba"], non_blocking=True)
-            out_nrm.copy_(r["normal"], non_blocking=True)
-            torch.cuda.synchronize()
+            # multi-GPU public API: pinned host samples in, results in pinned host memory
+            # (H2D, owner step and D2H pipelined in chunks; one deferred validation)
+            slab.transfer_host(q_xyz_host, k, {"idx": out_idx, "rgba": out_rgba, "normal": out_nrm},
+                               radius=w.radius)
 
     for _ in range(3):
         e2e_step()

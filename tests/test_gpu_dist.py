@@ -75,6 +75,21 @@ def _worker(rank, world, port, k, radius):
         assert gst.stats["path"] == "ghost-zone", gst.stats
         for name in ("idx", "d2", "rgba", "normal"):
             assert torch.equal(out[name], gout[name]), name
+        # host-buffer entry point: chunks pipelined over streams, one deferred validation
+        q_pin = torch.from_numpy(np.ascontiguousarray(V["ver"][own_q])).pin_memory()
+        host = {"idx": torch.empty((len(own_q), k), dtype=torch.int32).pin_memory(),
+                "rgba": torch.empty((len(own_q), 4), dtype=torch.uint8).pin_memory(),
+                "normal": torch.empty((len(own_q), 3), dtype=torch.float32).pin_memory()}
+        gst.transfer_host(q_pin, k, host, radius=radius, chunks=3)
+        for name in ("idx", "rgba", "normal"):
+            assert torch.equal(host[name], out[name].cpu()), "transfer_host " + name
+        # ... and when the deferred validation fails the batch is redone through the exchange
+        gst_n = pkg.dist.SlabTransfer(pkg.dist.CudaSlabEngine(gtree), own_box=own_box, halo=0.01)
+        for t in host.values():
+            t.zero_()
+        gst_n.transfer_host(q_pin, k, host, radius=radius, chunks=2)
+        for name in ("idx", "rgba", "normal"):
+            assert torch.equal(host[name], out[name].cpu()), "transfer_host fallback " + name
         # a ghost zone that is too narrow falls back to the exchange (duplicates dropped)
         gst2 = pkg.dist.SlabTransfer(pkg.dist.CudaSlabEngine(gtree), own_box=own_box, halo=0.01)
         gout2 = gst2.transfer(q, k, radius=radius, want_d2=True)
