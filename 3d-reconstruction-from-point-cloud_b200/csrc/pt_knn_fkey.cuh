@@ -76,6 +76,7 @@ knn_fkey_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     int hn = 0;                      // candidates held; the column is a max-heap once hn == k
     uint32_t root_key = FKEY_INF;    // key of the heap root (current k-th) -- meaningful once hn == k
     int pq_n = 0;
+    uint32_t lost = 0xffffffffu;   // smallest key of a queue entry that had to be given up
 
     // drop the queue entries that lie beyond the bound (it only shrinks, so they are dead) and
     // rebuild the heap in place
@@ -101,8 +102,33 @@ knn_fkey_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     };
     auto pq_push = [&](uint32_t key, uint32_t word) {
         if (pq_n == TPQ_CAP) {
-            pq_compact();      // only a queue full of live entries is an overflow
-            if (pq_n == TPQ_CAP) { overflow = true; return; }
+            pq_compact();
+            if (pq_n == TPQ_CAP) {
+                // still full of live entries: give up the least promising one (the largest key;
+                // in a min-heap it is among the leaves).  Exactness is kept by remembering the
+                // smallest key ever given up: if the final bound stays below it, no dropped
+                // subtree could have held a neighbour; otherwise the sample takes the fallback.
+                int mi = TPQ_CAP / 2;
+                uint32_t mk = pqk[mi * T_THREADS];
+                for (int e = TPQ_CAP / 2 + 1; e < TPQ_CAP; ++e) {
+                    const uint32_t ek = pqk[e * T_THREADS];
+                    if (ek > mk) { mk = ek; mi = e; }
+                }
+                if (key >= mk) { lost = min(lost, key); return; }
+                lost = min(lost, mk);
+                int i = mi;
+                while (i > 0) {
+                    int p = (i - 1) >> 1;
+                    uint32_t pk = pqk[p * T_THREADS];
+                    if (pk <= key) break;
+                    pqk[i * T_THREADS] = pk;
+                    pqw[i * T_THREADS] = pqw[p * T_THREADS];
+                    i = p;
+                }
+                pqk[i * T_THREADS] = key;
+                pqw[i * T_THREADS] = word;
+                return;
+            }
         }
         int i = pq_n++;
         while (i > 0) {
@@ -292,6 +318,8 @@ knn_fkey_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         }
     }
 
+    // a dropped queue entry matters only if its subtree could still reach inside the final bound
+    if (lost != 0xffffffffu && __uint_as_float(lost & ~0xfu) <= bound) overflow = true;
 #ifdef PT_STATS
     {
         unsigned v = (q < P.m && overflow) ? 1u : 0u, w = q < P.m ? 1u : 0u;

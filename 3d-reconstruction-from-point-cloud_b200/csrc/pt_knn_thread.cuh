@@ -178,6 +178,7 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     double root_d = INFINITY;   // heap root (current k-th) -- meaningful once hn == k
     int root_i = IDX_NONE;
     int pq_n = 0;
+    uint32_t lost = 0xffffffffu;   // smallest key of a queue entry that had to be given up
 
     // queue entry: key = bound bits with the low 4 mantissa bits replaced by the node's t-level
     // (still a valid, slightly smaller lower bound); word = unvisited-children mask << 23 | id
@@ -205,7 +206,32 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
                 }
             }
             pq_n = live;
-            if (pq_n == TPQ_CAP) { overflow = true; return; }
+            if (pq_n == TPQ_CAP) {
+                // still full of live entries: give up the least promising one (the largest key;
+                // in a min-heap it is among the leaves).  Exactness is kept by remembering the
+                // smallest key ever given up: if the final bound stays below it, no dropped
+                // subtree could have held a neighbour; otherwise the sample takes the fallback.
+                int mi = TPQ_CAP / 2;
+                uint32_t mk = pqk[mi * T_THREADS];
+                for (int e = TPQ_CAP / 2 + 1; e < TPQ_CAP; ++e) {
+                    const uint32_t ek = pqk[e * T_THREADS];
+                    if (ek > mk) { mk = ek; mi = e; }
+                }
+                if (key >= mk) { lost = min(lost, key); return; }
+                lost = min(lost, mk);
+                int i = mi;
+                while (i > 0) {
+                    int p = (i - 1) >> 1;
+                    uint32_t pk = pqk[p * T_THREADS];
+                    if (pk <= key) break;
+                    pqk[i * T_THREADS] = pk;
+                    pqw[i * T_THREADS] = pqw[p * T_THREADS];
+                    i = p;
+                }
+                pqk[i * T_THREADS] = key;
+                pqw[i * T_THREADS] = word;
+                return;
+            }
         }
         int i = pq_n++;
         while (i > 0) {
@@ -367,6 +393,8 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         if (hn == k) bound = __double2float_ru(fmin(root_d, r2));
     }
 
+    // a dropped queue entry matters only if its subtree could still reach inside the final bound
+    if (lost != 0xffffffffu && __uint_as_float(lost & ~0xfu) <= bound) overflow = true;
 #ifdef PT_STATS
     st_[8] = overflow ? 1 : 0;
     st_[9] = q < P.m ? 1 : 0;

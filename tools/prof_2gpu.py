@@ -4,6 +4,7 @@ the plain query on (a) the slab index without ids, (b) the ghost-augmented index
 import os, sys, math; sys.path.insert(0, "/root/repo")
 import torch, torch.distributed as dist, __graft_entry__ as ge
 pkg = ge.package()
+if os.environ.get("PT_VARIANT"): pkg.set_option("knn_variant", int(os.environ["PT_VARIANT"]))
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
 lr = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 w = pkg.synth.CONFIGS["cfg2"]; L = pkg.synth.L_DOMAIN; n = w.n_points; k = w.k

@@ -23,6 +23,7 @@ def run(name, p, a, qq=q):
         if it >= 3: ts.append(e0.elapsed_time(e1))
     st = pkg.api.debug_stats()
     per = {kk: round(v / 13 / mm, 3) for kk, v in st.items()} if st["samples"] else {}
+    if per: per["overflowed_per_launch"] = st["overflowed"] / 13; per["compactions_per_launch"] = st["compactions"] / 13
     print(f"{name}: {sum(ts)/len(ts):.4f} ms  n={p.shape[0]} m={mm} {per}", flush=True)
     t.close()
 

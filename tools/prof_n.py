@@ -8,6 +8,8 @@ q = pkg.synth.samples_device(w.gu, w.gv); m = q.shape[0]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 idx = torch.empty((m, k), dtype=torch.int32, device=dev); rgba = torch.empty((m, 4), dtype=torch.uint8, device=dev)
 nrm = torch.empty((m, 3), dtype=torch.float32, device=dev)
+import os
+if os.environ.get("PT_VARIANT"): pkg.set_option("knn_variant", int(os.environ["PT_VARIANT"]))
 out = []
 for nn in [int(a) for a in sys.argv[1:]] or [n, 49900000, 49000000, 50000000 - 32 * 7]:
     t = pkg.DeviceTree(pos[:nn], attrs[:nn])

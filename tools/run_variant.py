@@ -5,6 +5,8 @@ pkg = ge.package(); torch.cuda.set_device(0); dev = torch.device("cuda", 0)
 variant = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 w = pkg.synth.CONFIGS["cfg2"]; k = w.k
 pos, attrs = pkg.synth.cloud_device(w.n_points, w.seed)
+if len(sys.argv) > 2:       # optional: use only the first n points (size-sensitivity captures)
+    nn = int(sys.argv[2]); pos, attrs = pos[:nn].contiguous(), attrs[:nn].contiguous()
 q = pkg.synth.samples_device(w.gu, w.gv); m = q.shape[0]
 pkg.set_option("knn_variant", variant)
 tree = pkg.DeviceTree(pos, attrs)
