@@ -66,7 +66,7 @@ class BuildOpts(ctypes.Structure):
 class IndexInfo(ctypes.Structure):
     _fields_ = [("n_points", ctypes.c_uint64), ("n_leaves", ctypes.c_uint64),
                 ("n_levels", ctypes.c_int), ("coord_mode", ctypes.c_int),
-                ("device", ctypes.c_int), ("reserved_", ctypes.c_int),
+                ("device", ctypes.c_int), ("last_fallback_samples", ctypes.c_int),
                 ("bbox_lo", ctypes.c_double * 3), ("bbox_hi", ctypes.c_double * 3),
                 ("device_bytes", ctypes.c_uint64), ("build_ms", ctypes.c_float),
                 ("last_query_ms", ctypes.c_float), ("last_h2d_ms", ctypes.c_float),

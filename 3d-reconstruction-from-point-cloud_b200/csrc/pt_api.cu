@@ -255,6 +255,14 @@ int pt_index_get_info(const pt_index *ix, pt_index_info *info)
     info->n_levels = ix->pyr.n_levels;
     info->coord_mode = ix->coord_f64 ? PT_COORD_F64 : PT_COORD_F32;
     info->device = ix->device;
+    info->last_fallback_samples = -1;
+    if (ix->ws_ovf) {   // overflow counter of launch slot 0 (device word; this call may synchronise)
+        uint32_t c = 0;
+        if (cudaSetDevice(ix->device) == cudaSuccess &&
+            cudaMemcpy(&c, ix->ws_ovf, sizeof c, cudaMemcpyDeviceToHost) == cudaSuccess)
+            info->last_fallback_samples = (int)c;
+        cudaGetLastError();
+    }
     for (int a = 0; a < 3; ++a) { info->bbox_lo[a] = ix->bb_lo[a]; info->bbox_hi[a] = ix->bb_hi[a]; }
     info->device_bytes = ix->device_bytes;
     info->build_ms = ix->build_ms;

@@ -422,10 +422,10 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
     }
     int variant = opt_knn_variant();
     if (variant < 0) {
-        // auto: the fp32-keyed kernel keeps 30 % more warps resident at k > 16 (measured +22 % at
-        // cfg4) and is 5-7 % ahead once a launch spans several waves; the thread kernel wins on
-        // small batches (cfg2: 3 waves) -- DESIGN.md section 4
-        variant = (qp.k > 16 || qp.m >= 320000u) ? 4 : 2;
+        // auto: at k > 16 the fp32-keyed kernel's smaller entries keep far more warps resident
+        // (measured +21 % at cfg4's k = 32); at k <= 16 the thread kernel is as fast or faster
+        // on every workload shape -- DESIGN.md section 4
+        variant = qp.k > 16 ? 4 : 2;
     }
     return ix->coord_f64 ? launch_with_fallback<PointD>(ix, qp, variant, s, slot)
                          : launch_with_fallback<PointF>(ix, qp, variant, s, slot);

@@ -353,15 +353,16 @@ knn_fkey_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
 
 static inline size_t fkey_kernel_smem(int k)
 {
-    // entries [k] + pending [TPD_CAP] (8 B each) + queue [TPQ_CAP] (8 B); the epilogue's
-    // (d2, index) columns, 12 B * k, fit inside it
-    return (size_t)T_THREADS * ((size_t)(k + TPD_CAP) * 8 + (size_t)TPQ_CAP * 8);
+    // entries [k] + pending [TPD_CAP] (8 B each) + queue [TPQ_CAP] (8 B), and at least the
+    // epilogue's (d2, index) columns, 12 B * k
+    size_t per = (size_t)(k + TPD_CAP) * 8 + (size_t)TPQ_CAP * 8;
+    if (per < (size_t)k * 12) per = (size_t)k * 12;
+    return (size_t)T_THREADS * per;
 }
 
 template <typename PT>
 static int launch_fkey(const QueryParams &qp, uint32_t *count, uint32_t *list, cudaStream_t s)
 {
-    static_assert((PT_MAX_K + TPD_CAP) * 8 + TPQ_CAP * 8 >= PT_MAX_K * 12, "epilogue: (d2, index) columns must fit");
     static bool attr_set[2] = {false, false};
     const int which = sizeof(PT) == 32;
     if (!attr_set[which]) {

@@ -39,7 +39,10 @@ __device__ unsigned long long g_stats[16];
 constexpr int T_THREADS = PT_T_THREADS;
 constexpr int T_LOG = 3;
 #ifndef PT_TPQ_CAP
-#define PT_TPQ_CAP 24
+// queue entries per sample.  A full queue gives up its least promising entry (see pq_push), so a
+// small queue is exact and cheap: 8 already works (a few fallbacks per million samples), 12 had
+// none on any workload shape, and every 8 entries less is one more resident warp per SM
+#define PT_TPQ_CAP 12
 #endif
 #ifndef PT_T_BATCH_BOXES
 #define PT_T_BATCH_BOXES 1
@@ -141,8 +144,11 @@ __device__ __forceinline__ void emit_sample(const QueryParams &P, uint32_t q, do
     }
 }
 
+#ifndef PT_T_MIN_BLOCKS
+#define PT_T_MIN_BLOCKS 1
+#endif
 template <typename PT>
-__global__ void __launch_bounds__(T_THREADS)
+__global__ void __launch_bounds__(T_THREADS, PT_T_MIN_BLOCKS)
 knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
 {
     extern __shared__ __align__(16) unsigned char t_smem[];

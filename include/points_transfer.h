@@ -75,7 +75,8 @@ typedef struct pt_index_info {
     int      n_levels;       /* box-pyramid levels */
     int      coord_mode;     /* PT_COORD_F32 or PT_COORD_F64 actually used */
     int      device;
-    int      reserved_;
+    int      last_fallback_samples; /* samples the last query launch (slot 0) handed to the exact
+                                       warp kernel (queue proof obligation not met); -1 unknown */
     double   bbox_lo[3], bbox_hi[3];
     uint64_t device_bytes;   /* resident after the build */
     float    build_ms;       /* device time of the last build (CUDA events) */

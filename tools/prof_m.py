@@ -3,7 +3,7 @@ import sys; sys.path.insert(0, "/root/repo")
 import torch, __graft_entry__ as ge
 pkg = ge.package(); torch.cuda.set_device(0); dev = torch.device("cuda", 0)
 variants = [int(a) for a in sys.argv[1:]] or [2, 4]
-GRIDS = (448, 896, 1344)
+GRIDS = (448, 896)
 w = pkg.synth.CONFIGS["cfg2"]; k = w.k
 pos, attrs = pkg.synth.cloud_device(w.n_points, w.seed)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -21,6 +21,6 @@ for g in GRIDS:
             e0.record(); tree.query(q, k, idx=idx, rgba=rgba, normal=nrm); e1.record(); torch.cuda.synchronize()
             if it >= 3: ts.append(e0.elapsed_time(e1))
         t = sum(ts) / len(ts)
-        line += f"  v{v}: {t:.4f} ms {m / t / 1e3:7.1f} Msamples/s"
+        line += f"  v{v}: {t:.4f} ms {m / t / 1e3:7.1f} Msamples/s fb={tree.info().last_fallback_samples}"
     print(line, flush=True)
 tree.close()

@@ -26,7 +26,8 @@ for variant in variants:
         if it >= 3: ts.append(e0.elapsed_time(e1))
     st = pkg.api.debug_stats()
     per = {kk: round(v / 13 / m, 3) for kk, v in st.items()} if st["samples"] else {}
-    print(f"{cfg} variant {variant}: {sum(ts)/len(ts):.4f} ms (min {min(ts):.4f})  m={m} k={k} {per}", flush=True)
+    print(f"{cfg} variant {variant}: {sum(ts)/len(ts):.4f} ms (min {min(ts):.4f})  m={m} k={k} "
+          f"fallback={tree.info().last_fallback_samples} {per}", flush=True)
 a, b = res[variants[0]], res[variants[-1]]
 for name, x, y in zip(("idx", "d2", "rgba", "normal"), a, b):
     same = bool(torch.equal(x, y))
