@@ -60,7 +60,7 @@ def algorithmic_bytes_per_sample(k):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the query kernel from the
 # `ncu --set full` capture committed under profiles/ (r1_knn_thread_kernel_ncu_summary.txt):
 # valid only for the workload / kernel it was captured on.
-NCU_TRAFFIC = {("cfg2", 16, 2): 783.25e6 + 17.63e6}
+NCU_TRAFFIC = {("cfg2", 16, 2): 815.12e6 + 17.60e6}
 
 
 def measured_peaks():
