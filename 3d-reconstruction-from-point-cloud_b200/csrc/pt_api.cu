@@ -42,7 +42,7 @@ int map_cuda_error(cudaError_t e)
 int opt_knn_variant() { return g_knn_variant.load(); }
 int opt_order() { return g_order.load(); }
 int opt_sort() { return g_sort.load(); }
-static std::atomic<int> g_host_chunks{3};   // host-buffer API: pipeline chunks per call (3 streams)
+static std::atomic<int> g_host_chunks{8};   // host-buffer API: pipeline chunks per call (one stream each, up to 16)
 int opt_host_chunks() { return g_host_chunks.load(); }
 static std::atomic<int> g_smem_pad{0};   // diagnosis: extra dynamic smem per query block (occupancy probe)
 int opt_smem_pad() { return g_smem_pad.load(); }
@@ -351,7 +351,7 @@ int pt_halo_merge_device(pt_cand *own_cand, const pt_cand *back, const int32_t *
                              normal_out, (cudaStream_t)stream);
 }
 
-// Host-buffer query.  Large batches are cut into chunks that are pipelined over three streams so
+// Host-buffer query.  Large batches are cut into chunks, each on its own stream (up to 16), so
 // the H2D copy of the 80-byte records, the kernels and the D2H copy of the results overlap
 // (pinned caller buffers make the copies truly asynchronous; pageable ones still work).
 static int host_query(pt_index *ix, const void *queries, size_t m, int k, double radius,
@@ -374,7 +374,7 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
     PT_TRY(grow(&ix->ws_out, &ix->ws_out_bytes, total ? total : 16));
     char *o = (char *)ix->ws_out;
 
-    constexpr int NCS = 3;
+    constexpr int NCS = 16;  // chunk streams (a chunk kernel has a ~0.27 ms latency floor, so chunks must overlap)
     size_t chunk = m;
     const size_t want = (size_t)opt_host_chunks();
     if (m >= 32768 && want > 1) chunk = (((m + want - 1) / want) + 31) & ~(size_t)31;

@@ -27,8 +27,8 @@ struct pt_index {
     void  *ws_out = nullptr;   size_t ws_out_bytes = 0;    // idx | d2 | rgba | normal
     void  *ws_ovf = nullptr;   size_t ws_ovf_bytes = 0;    // queue-overflow count + sample list,
     uint32_t ovf_slot_words = 0;                           //   one slot per concurrent launch
-    cudaStream_t cs[3]{};                                  // chunk streams of the host-buffer API
-    cudaEvent_t  cev[3]{};
+    cudaStream_t cs[16]{};                                  // chunk streams of the host-buffer API
+    cudaEvent_t  cev[16]{};
 };
 
 namespace pt {
