@@ -44,7 +44,7 @@ SYNTH_HEIGHTFIELD, SYNTH_SKEWED = 0, 1
 # Every symbol include/points_transfer.h and include/pt_synth.h declare.
 ABI_SYMBOLS = (
     "pt_version", "pt_status_string", "pt_device_count", "pt_index_build", "pt_index_free",
-    "pt_index_get_info", "pt_knn", "pt_transfer", "pt_index_build_device", "pt_query_device",
+    "pt_index_get_info", "pt_knn", "pt_transfer", "pt_transfer_slab", "pt_index_build_device", "pt_query_device",
     "pt_merge_device", "pt_halo_route_device", "pt_halo_prepare_device",
     "pt_halo_merge_device", "pt_ghost_check_device", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
     "pt_synth_cloud_device", "pt_synth_samples_device", "pt_synth_pack_points_device",
@@ -108,6 +108,9 @@ def lib():
     L.pt_knn.argtypes = [vp, vp, sz, i32, dbl, vp, vp]
     L.pt_transfer.restype = i32
     L.pt_transfer.argtypes = [vp, vp, sz, i32, dbl, vp, vp, vp, vp]
+    L.pt_transfer_slab.restype = i32
+    L.pt_transfer_slab.argtypes = [vp, vp, i32, sz, i32, dbl, vp, i32, i32, dbl, vp, vp, vp, vp,
+                                   ctypes.POINTER(i32)]
     L.pt_index_build_device.restype = i32
     L.pt_index_build_device.argtypes = [vp, i32, vp, vp, sz, i32, ctypes.POINTER(vp)]
     L.pt_query_device.restype = i32
@@ -311,6 +314,20 @@ class Tree:
                                  _np_ptr(out.get("idx")), _np_ptr(out.get("d2")),
                                  _np_ptr(out["rgba"]), _np_ptr(out["normal"])), "pt_transfer")
         return out
+
+
+    def transfer_slab(self, queries_ptr, queries_are_xyz, m, k, radius, boxes6, rank, halo,
+                      idx_ptr, rgba_ptr, normal_ptr, d2_ptr=None):
+        """pt_transfer_slab on raw host pointers (ints): one slab's pipelined host-buffer step
+        with the ghost-zone check fused in.  boxes6: float64 numpy [R,6].  Returns True when the
+        results are final (no sample may leave the ghost zone towards another slab)."""
+        boxes6 = np.ascontiguousarray(boxes6, dtype=np.float64)
+        need = ctypes.c_int32(0)
+        _check(lib().pt_transfer_slab(self._h, queries_ptr, 1 if queries_are_xyz else 0, int(m),
+                                      int(k), _radius(radius), _np_ptr(boxes6), boxes6.shape[0],
+                                      int(rank), float(halo), idx_ptr, d2_ptr, rgba_ptr,
+                                      normal_ptr, ctypes.byref(need)), "pt_transfer_slab")
+        return need.value == 0
 
 
 class K_neighbor_search:

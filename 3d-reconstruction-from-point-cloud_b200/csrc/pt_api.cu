@@ -354,25 +354,44 @@ int pt_halo_merge_device(pt_cand *own_cand, const pt_cand *back, const int32_t *
 // Host-buffer query.  Large batches are cut into chunks, each on its own stream (up to 16), so
 // the H2D copy of the 80-byte records, the kernels and the D2H copy of the results overlap
 // (pinned caller buffers make the copies truly asynchronous; pageable ones still work).
+// Ghost-zone check of a slab index (pt_transfer_slab): host copies of the slabs' boxes.
+struct GhostCheck {
+    const double *boxes;   // n_ranks x 6, host
+    int n_ranks, self;
+    double halo;
+    int *needs_exchange;   // out
+};
+
 static int host_query(pt_index *ix, const void *queries, size_t m, int k, double radius,
-                      int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out)
+                      int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out,
+                      bool queries_are_xyz = false, const GhostCheck *ghost = nullptr)
 {
     if (!ix || (!queries && m) || m > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
     if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
     if ((rgba_out || normal_out) && !ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
+    if (ghost && ghost->needs_exchange) *ghost->needs_exchange = 0;
     if (m == 0) return PT_OK;
     PT_CUDA(cudaSetDevice(ix->device));
     cudaStream_t s = ix->stream;
     const size_t mk = m * (size_t)k;
+    const bool need_d2 = d2_out || ghost;      // the ghost check reads the k-th d2 on the device
     // output workspace layout: d2 | idx | normal | rgba (descending alignment)
-    size_t off_d2 = 0, off_idx = off_d2 + (d2_out ? mk * 8 : 0);
+    size_t off_d2 = 0, off_idx = off_d2 + (need_d2 ? mk * 8 : 0);
     size_t off_nrm = off_idx + (idx_out ? mk * 4 : 0);
     size_t off_rgba = off_nrm + (normal_out ? m * 12 : 0);
     size_t total = off_rgba + (rgba_out ? m * 4 : 0);
-    PT_TRY(grow(&ix->ws_raw, &ix->ws_raw_bytes, m * PT_POINT_STRIDE));
+    if (!queries_are_xyz) PT_TRY(grow(&ix->ws_raw, &ix->ws_raw_bytes, m * PT_POINT_STRIDE));
     PT_TRY(grow(&ix->ws_q, &ix->ws_q_bytes, m * 24));
-    PT_TRY(grow(&ix->ws_out, &ix->ws_out_bytes, total ? total : 16));
+    // tail of the output workspace: the slabs' boxes and the check flag of the ghost zone
+    const size_t off_boxes = (total + 15) & ~(size_t)15;
+    const size_t off_flag = off_boxes + (ghost ? sizeof(double) * 6 * (size_t)ghost->n_ranks : 0);
+    PT_TRY(grow(&ix->ws_out, &ix->ws_out_bytes, off_flag + 16));
     char *o = (char *)ix->ws_out;
+    if (ghost) {
+        PT_CUDA(cudaMemcpyAsync(o + off_boxes, ghost->boxes, sizeof(double) * 6 * (size_t)ghost->n_ranks,
+                                cudaMemcpyHostToDevice, s));
+        PT_CUDA(cudaMemsetAsync(o + off_flag, 0, sizeof(uint32_t), s));
+    }
 
     constexpr int NCS = 16;  // chunk streams (a chunk kernel has a ~0.27 ms latency floor, so chunks must overlap)
     size_t chunk = m;
@@ -393,17 +412,27 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
         cudaStream_t st = ix->cs[si];
         const size_t c0 = (size_t)c * chunk;
         const size_t cm = m - c0 < chunk ? m - c0 : chunk;
-        char *raw = (char *)ix->ws_raw + c0 * PT_POINT_STRIDE;
         double *qd = (double *)ix->ws_q + 3 * c0;
-        PT_CUDA(cudaMemcpyAsync(raw, (const char *)queries + c0 * PT_POINT_STRIDE,
-                                cm * PT_POINT_STRIDE, cudaMemcpyHostToDevice, st));
-        PT_TRY(unpack_queries_aos(raw, cm, qd, st));
+        if (queries_are_xyz) {
+            PT_CUDA(cudaMemcpyAsync(qd, (const double *)queries + 3 * c0, cm * 24,
+                                    cudaMemcpyHostToDevice, st));
+        } else {
+            char *raw = (char *)ix->ws_raw + c0 * PT_POINT_STRIDE;
+            PT_CUDA(cudaMemcpyAsync(raw, (const char *)queries + c0 * PT_POINT_STRIDE,
+                                    cm * PT_POINT_STRIDE, cudaMemcpyHostToDevice, st));
+            PT_TRY(unpack_queries_aos(raw, cm, qd, st));
+        }
         PT_TRY(query_device_slot(ix, qd, cm, k, radius, nullptr,
                                  idx_out ? (int32_t *)(o + off_idx) + c0 * k : nullptr,
-                                 d2_out ? (double *)(o + off_d2) + c0 * k : nullptr,
+                                 need_d2 ? (double *)(o + off_d2) + c0 * k : nullptr,
                                  rgba_out ? (uint8_t *)(o + off_rgba) + c0 * 4 : nullptr,
                                  normal_out ? (float *)(o + off_nrm) + c0 * 3 : nullptr, nullptr,
                                  st, si));
+        if (ghost)
+            PT_TRY(launch_ghost_check(qd, (double *)(o + off_d2) + c0 * k, (uint32_t)cm, k,
+                                      radius_to_r2(radius), (const double *)(o + off_boxes),
+                                      ghost->n_ranks, ghost->self, ghost->halo,
+                                      (uint32_t *)(o + off_flag), st));
         if (d2_out) PT_CUDA(cudaMemcpyAsync(d2_out + c0 * k, (double *)(o + off_d2) + c0 * k, cm * k * 8, cudaMemcpyDeviceToHost, st));
         if (idx_out) PT_CUDA(cudaMemcpyAsync(idx_out + c0 * k, (int32_t *)(o + off_idx) + c0 * k, cm * k * 4, cudaMemcpyDeviceToHost, st));
         if (normal_out) PT_CUDA(cudaMemcpyAsync(normal_out + c0 * 3, (float *)(o + off_nrm) + c0 * 3, cm * 12, cudaMemcpyDeviceToHost, st));
@@ -413,8 +442,11 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
         PT_CUDA(cudaEventRecord(ix->cev[i], ix->cs[i]));
         PT_CUDA(cudaStreamWaitEvent(s, ix->cev[i], 0));
     }
+    uint32_t flag = 0;
+    if (ghost) PT_CUDA(cudaMemcpyAsync(&flag, o + off_flag, sizeof flag, cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaEventRecord(ix->ev[3], s));
     PT_CUDA(cudaStreamSynchronize(s));
+    if (ghost && ghost->needs_exchange) *ghost->needs_exchange = flag ? 1 : 0;
     ix->last_h2d_ms = 0.f;          // overlapped with the kernels: only the total is meaningful
     ix->last_d2h_ms = 0.f;
     cudaEventElapsedTime(&ix->last_query_ms, ix->ev[0], ix->ev[3]);
@@ -433,6 +465,18 @@ int pt_transfer(pt_index *index, const void *queries, size_t m, int k, double ra
 {
     if ((!rgba_out && !normal_out) && m) return PT_ERR_INVALID_ARG;
     return host_query(index, queries, m, k, radius, idx_out, d2_out, rgba_out, normal_out);
+}
+
+int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, size_t m, int k,
+                     double radius, const double *boxes, int n_ranks, int self, double halo,
+                     int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out,
+                     int *needs_exchange)
+{
+    if (!boxes || !needs_exchange || n_ranks < 1 || n_ranks > 4096 || self < 0 || self >= n_ranks)
+        return PT_ERR_INVALID_ARG;
+    GhostCheck g{boxes, n_ranks, self, halo, needs_exchange};
+    return host_query(index, queries, m, k, radius, idx_out, d2_out, rgba_out, normal_out,
+                      queries_are_xyz != 0, &g);
 }
 
 }  // extern "C"

@@ -358,11 +358,13 @@ class SlabTransfer:
     def transfer_host(self, q_host, k, out, radius=None, chunks=3):
         """Host-buffer entry point of the sharded path: ``q_host`` float64 [m,3] (pinned for true
         overlap) holds the samples this rank owns, ``out`` maps "idx" [m,k] int32, "rgba" [m,4]
-        uint8, "normal" [m,3] float32 to (pinned) host tensors that receive the results.  The
-        batch is cut into ``chunks`` pieces pipelined over CUDA streams -- H2D of the samples,
-        the owner step (no collective in the ghost-zone steady state) and the D2H of the results
-        overlap -- with ONE deferred validation (one tiny all-reduce) at the end; if that fails
-        the batch is redone through the exchange path.  Returns after everything has landed."""
+        uint8, "normal" [m,3] float32 to (pinned) host tensors that receive the results.
+        On the CUDA engine this is one call of the C ABI (``pt_transfer_slab``: the H2D copy of
+        the samples, the owner step with the ghost-zone check and the D2H copy of the results are
+        pipelined chunk by chunk inside the library) followed by ONE tiny all-reduce in which the
+        ranks agree that nobody needs the exchange; otherwise (or on other engines, through
+        ``chunks`` torch-stream pieces) the batch is redone through the exchange path.
+        Returns after everything has landed."""
         m = q_host.shape[0]
         dev = self.device
         if self.world == 1 or self.halo is None or not getattr(self.engine, "fast", False) or m == 0:
@@ -372,30 +374,49 @@ class SlabTransfer:
             if dev.type == "cuda":
                 torch.cuda.synchronize(dev)
             return
-        chunks = max(1, min(int(chunks), m))
-        step = -(-m // chunks)
-        if getattr(self, "_host_streams", None) is None:
-            self._host_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
-        cur = torch.cuda.current_stream(dev)
-        keep = []
-        for c in range(chunks):
-            lo, hi = c * step, min(m, (c + 1) * step)
-            st = self._host_streams[c % len(self._host_streams)]
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                qd = q_host[lo:hi].to(dev, non_blocking=True)
-                r = self.transfer(qd, k, radius=radius, validate=False)
-                for name in ("idx", "rgba", "normal"):
-                    out[name][lo:hi].copy_(r[name], non_blocking=True)
-                keep.append((qd, r))
-        for st in self._host_streams:
-            cur.wait_stream(st)
-        torch.cuda.synchronize(dev)
-        if not self.validate():            # some sample needed the exchange: exact path, whole batch
-            r = self.transfer(q_host.to(dev, non_blocking=True), k, radius=radius)
-            for name in ("idx", "rgba", "normal"):
-                out[name].copy_(r[name], non_blocking=True)
+        tree = getattr(self.engine, "tree", None)
+        if tree is not None and hasattr(tree, "transfer_slab") and q_host.dtype == torch.float64 \
+                and q_host.is_contiguous() and all(out[n].is_contiguous() for n in ("idx", "rgba", "normal")):
+            # the C host path: H2D / owner step + ghost check / D2H pipelined chunk by chunk
+            # inside the library (pt_transfer_slab), then ONE agreement across the ranks
+            if getattr(self, "_boxes6_host", None) is None:
+                self._boxes6_host = self.boxes6.cpu().numpy()
+            ok = tree.transfer_slab(q_host.data_ptr(), True, m, k, radius, self._boxes6_host,
+                                    self.rank, self.halo, out["idx"].data_ptr(),
+                                    out["rgba"].data_ptr(), out["normal"].data_ptr())
+            bad = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+            if int(bad.item()) == 0:
+                self.stats = {"crossing": 0, "sent": 0, "received": 0, "path": "ghost-zone (host)",
+                              "halo": self.halo}
+                return
+        else:
+            chunks = max(1, min(int(chunks), m))
+            step = -(-m // chunks)
+            if getattr(self, "_host_streams", None) is None:
+                self._host_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+            cur = torch.cuda.current_stream(dev)
+            keep = []
+            for c in range(chunks):
+                lo, hi = c * step, min(m, (c + 1) * step)
+                st = self._host_streams[c % len(self._host_streams)]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    qd = q_host[lo:hi].to(dev, non_blocking=True)
+                    r = self.transfer(qd, k, radius=radius, validate=False)
+                    for name in ("idx", "rgba", "normal"):
+                        out[name][lo:hi].copy_(r[name], non_blocking=True)
+                    keep.append((qd, r))
+            for st in self._host_streams:
+                cur.wait_stream(st)
             torch.cuda.synchronize(dev)
+            if self.validate():
+                return
+        # some sample needed the exchange: exact path, whole batch
+        r = self.transfer(q_host.to(dev, non_blocking=True), k, radius=radius)
+        for name in ("idx", "rgba", "normal"):
+            out[name].copy_(r[name], non_blocking=True)
+        torch.cuda.synchronize(dev)
 
     def transfer(self, q, k, radius=None, want_d2=False, validate=True):
         """q float64 [m,3] on the engine's device (samples owned by this rank).

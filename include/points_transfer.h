@@ -179,6 +179,18 @@ int pt_ghost_check_device(const double *queries_xyz, const double *d2, size_t m,
                           double radius, const double *boxes, int n_ranks, int self,
                           double halo, uint32_t *flag, void *stream);
 
+/* Host-buffer step of ONE slab of a sharded cloud whose index also holds the other slabs' points
+ * within `halo` of its box (ghost zone): pt_transfer on the samples this slab owns plus the
+ * pt_ghost_check_device test, fused per pipeline chunk.  queries: m Point records (80 B), or
+ * m x 3 doubles when queries_are_xyz != 0.  boxes: n_ranks x 6 doubles in HOST memory.
+ * *needs_exchange = 1 when some sample's k-th-neighbour ball may leave the ghost zone towards
+ * another slab: the results of such a call are not final and the caller runs the exchange
+ * (DESIGN.md section 6).  Ids are the index's global ids. */
+int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, size_t m, int k,
+                     double radius, const double *boxes, int n_ranks, int self, double halo,
+                     int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out,
+                     int *needs_exchange);
+
 /* Tuning / introspection. */
 /* Options: "knn_variant" (-1 auto [default], 4 fp32-keyed thread kernel, 2 thread kernel,
  * 1 octet, 0 warp), "order" (0 Morton, 1 Hilbert, 2 Hilbert + kd refinement [default]),
