@@ -44,6 +44,8 @@ int opt_order() { return g_order.load(); }
 int opt_sort() { return g_sort.load(); }
 static std::atomic<int> g_host_chunks{8};   // host-buffer API: pipeline chunks per call (one stream each, up to 16)
 int opt_host_chunks() { return g_host_chunks.load(); }
+static std::atomic<int> g_queue_cap{1 << 20};   // tests: shrink the per-sample queue (exactness under spilling)
+int opt_queue_cap() { return g_queue_cap.load(); }
 static std::atomic<int> g_smem_pad{0};   // diagnosis: extra dynamic smem per query block (occupancy probe)
 int opt_smem_pad() { return g_smem_pad.load(); }
 
@@ -54,6 +56,7 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "order")) { g_order.store(value); return PT_OK; }
     if (!strcmp(name, "sort")) { g_sort.store(value); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }
+    if (!strcmp(name, "queue_cap")) { g_queue_cap.store(value < 2 ? 2 : value); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { g_host_chunks.store(value < 1 ? 1 : (value > 64 ? 64 : value)); return PT_OK; }
     if (!strcmp(name, "verbose")) { g_verbose.store(value ? 1 : 0); return PT_OK; }
     return PT_ERR_INVALID_ARG;
@@ -65,6 +68,7 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "order")) { *value = g_order.load(); return PT_OK; }
     if (!strcmp(name, "sort")) { *value = g_sort.load(); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { *value = g_smem_pad.load(); return PT_OK; }
+    if (!strcmp(name, "queue_cap")) { *value = g_queue_cap.load(); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { *value = g_host_chunks.load(); return PT_OK; }
     if (!strcmp(name, "verbose")) { *value = verbose() ? 1 : 0; return PT_OK; }
     return PT_ERR_INVALID_ARG;
@@ -139,6 +143,7 @@ static void fill_params(const pt_index *ix, QueryParams &qp)
     qp.n_leaves = ix->n_leaves;
     qp.w_levels = ix->w_levels;
     qp.t_levels = ix->t_levels;
+    qp.pq_cap = opt_queue_cap();
 }
 
 }  // namespace pt

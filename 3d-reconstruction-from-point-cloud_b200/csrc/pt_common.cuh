@@ -73,6 +73,7 @@ struct QueryParams {
     uint32_t       n_leaves;
     int            w_levels;   // number of 32-wide levels used by the warp traversal
     int            t_levels;   // number of 8-wide levels used by the thread traversal
+    int            pq_cap;     // queue entries a sample may hold (<= the compiled capacity)
     const double  *queries;    // m * 3
     const double  *r2_per_query;
     uint32_t       m;

@@ -100,6 +100,7 @@ int  opt_knn_variant();
 int  opt_order();
 int  opt_sort();
 int  opt_smem_pad();
+int  opt_queue_cap();
 int  debug_stats(unsigned long long *out16, int reset);
 
 }  // namespace pt

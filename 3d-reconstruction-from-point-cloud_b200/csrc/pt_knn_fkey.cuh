@@ -43,7 +43,7 @@ __device__ __forceinline__ void fheap_sift(unsigned long long *he, int pos, int 
 }
 
 #ifndef PT_FKEY_MIN_BLOCKS
-#define PT_FKEY_MIN_BLOCKS 1
+#define PT_FKEY_MIN_BLOCKS 20
 #endif
 template <typename PT>
 __global__ void __launch_bounds__(T_THREADS, PT_FKEY_MIN_BLOCKS)
@@ -77,6 +77,7 @@ knn_fkey_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     uint32_t root_key = FKEY_INF;    // key of the heap root (current k-th) -- meaningful once hn == k
     int pq_n = 0;
     uint32_t lost = 0xffffffffu;   // smallest key of a queue entry that had to be given up
+    const int qcap = min(max(P.pq_cap, 2), TPQ_CAP);   // runtime cap <= layout (tests shrink it)
 
     // drop the queue entries that lie beyond the bound (it only shrinks, so they are dead) and
     // rebuild the heap in place
@@ -101,16 +102,17 @@ knn_fkey_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         pq_n = live;
     };
     auto pq_push = [&](uint32_t key, uint32_t word) {
-        if (pq_n == TPQ_CAP) {
+        if (pq_n == qcap) {
             pq_compact();
-            if (pq_n == TPQ_CAP) {
+            if (pq_n == qcap) {
                 // still full of live entries: give up the least promising one (the largest key;
                 // in a min-heap it is among the leaves).  Exactness is kept by remembering the
                 // smallest key ever given up: if the final bound stays below it, no dropped
                 // subtree could have held a neighbour; otherwise the sample takes the fallback.
-                int mi = TPQ_CAP / 2;
+                int mi = qcap / 2;
                 uint32_t mk = pqk[mi * T_THREADS];
-                for (int e = TPQ_CAP / 2 + 1; e < TPQ_CAP; ++e) {
+#pragma unroll 1
+                for (int e = qcap / 2 + 1; e < qcap; ++e) {
                     const uint32_t ek = pqk[e * T_THREADS];
                     if (ek > mk) { mk = ek; mi = e; }
                 }

@@ -145,7 +145,7 @@ __device__ __forceinline__ void emit_sample(const QueryParams &P, uint32_t q, do
 }
 
 #ifndef PT_T_MIN_BLOCKS
-#define PT_T_MIN_BLOCKS 1
+#define PT_T_MIN_BLOCKS 17      // = the shared-memory limit at k = 16: keeps the register count from capping occupancy
 #endif
 template <typename PT>
 __global__ void __launch_bounds__(T_THREADS, PT_T_MIN_BLOCKS)
@@ -185,17 +185,19 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     int root_i = IDX_NONE;
     int pq_n = 0;
     uint32_t lost = 0xffffffffu;   // smallest key of a queue entry that had to be given up
+    const int qcap = min(max(P.pq_cap, 2), TPQ_CAP);   // runtime cap <= layout (tests shrink it)
 
     // queue entry: key = bound bits with the low 4 mantissa bits replaced by the node's t-level
     // (still a valid, slightly smaller lower bound); word = unvisited-children mask << 23 | id
     auto pq_push = [&](uint32_t key, uint32_t word) {
         PT_STAT(2, 1);
-        if (pq_n == TPQ_CAP) {
+        if (pq_n == qcap) {
             PT_STAT(4, 1);
             // full: the bound only decreases, so entries above it are dead -- drop them and
             // rebuild the heap (rare); only a queue full of live entries is an overflow
             int live = 0;
-            for (int e = 0; e < TPQ_CAP; ++e) {
+#pragma unroll 1
+            for (int e = 0; e < qcap; ++e) {
                 const uint32_t ek = pqk[e * T_THREADS], ew = pqw[e * T_THREADS];
                 if (__uint_as_float(ek & ~0xfu) <= bound) {
                     int i = live++;
@@ -212,14 +214,15 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
                 }
             }
             pq_n = live;
-            if (pq_n == TPQ_CAP) {
+            if (pq_n == qcap) {
                 // still full of live entries: give up the least promising one (the largest key;
                 // in a min-heap it is among the leaves).  Exactness is kept by remembering the
                 // smallest key ever given up: if the final bound stays below it, no dropped
                 // subtree could have held a neighbour; otherwise the sample takes the fallback.
-                int mi = TPQ_CAP / 2;
+                int mi = qcap / 2;
                 uint32_t mk = pqk[mi * T_THREADS];
-                for (int e = TPQ_CAP / 2 + 1; e < TPQ_CAP; ++e) {
+#pragma unroll 1
+                for (int e = qcap / 2 + 1; e < qcap; ++e) {
                     const uint32_t ek = pqk[e * T_THREADS];
                     if (ek > mk) { mk = ek; mi = e; }
                 }

@@ -195,7 +195,8 @@ int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, 
 /* Options: "knn_variant" (-1 auto [default], 4 fp32-keyed thread kernel, 2 thread kernel,
  * 1 octet, 0 warp), "order" (0 Morton, 1 Hilbert, 2 Hilbert + kd refinement [default]),
  * "sort" (1 hand-written radix sort [default], 0 cub), "host_chunks" (pipeline chunks of the
- * host-buffer API, default 8), "verbose", "smem_pad" (diagnosis). */
+ * host-buffer API, default 8), "queue_cap" (tests: per-sample traversal queue entries, at most
+ * the compiled 12), "verbose", "smem_pad" (diagnosis). */
 int pt_set_option(const char *name, int value);
 int pt_get_option(const char *name, int *value);
 /* Work counters of the query kernel since the last reset (16 words; all zero unless the library

@@ -34,6 +34,7 @@ def _check_blend(got_rgba, got_nrm, ref_rgba, ref_nrm):
 def _default_options(pkg):
     yield
     pkg.set_option("knn_variant", -1)     # auto (the default)
+    pkg.set_option("queue_cap", 1 << 20)  # the compiled capacity
     pkg.set_option("order", 2)
 
 
@@ -217,6 +218,38 @@ def test_queue_overflow_falls_back_exactly(pkg, pto, torch_cuda):
             out = tree.transfer(Q, k, want_idx=True, want_d2=True)
         assert np.array_equal(out["idx"], ref_idx) and np.array_equal(out["d2"], ref_d2)
         _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
+
+
+@pytest.mark.parametrize("variant", [2, 4])
+@pytest.mark.parametrize("cap", [2, 3, 5, 8])
+def test_tiny_queue_stays_exact(cap, variant, pkg, pto, golden_dir, torch_cuda):
+    """A full traversal queue gives up its least promising entry and remembers the smallest key
+    it dropped; the sample is final only if the final bound stays below that key, otherwise it is
+    re-run by the exact warp kernel.  Results must therefore be exact for ANY capacity."""
+    pkg.set_option("knn_variant", variant)
+    pkg.set_option("queue_cap", cap)
+    P = pkg.synth.cloud_host(200_000, seed=31 + cap, side=70.0)
+    V = pkg.synth.samples_host(64, side=70.0)
+    for k in (8, 20):
+        ref_idx, ref_d2 = pto.KdTree(P).knn(V, k, exact_ties=True)
+        ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+        with pkg.Tree(P) as tree:
+            out = tree.transfer(V, k, want_idx=True, want_d2=True)
+            fallbacks = tree.info().last_fallback_samples
+        assert np.array_equal(out["idx"], ref_idx) and np.array_equal(out["d2"], ref_d2)
+        _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
+        if cap <= 3:
+            assert fallbacks > 0        # the give-up path and its fallback were exercised
+    for name in ("skewed", "lattice_ties", "duplicates", "radius_bounded"):
+        z = np.load(os.path.join(golden_dir, name + ".npz"))
+        Pg = pkg.make_points(z["xyz"], normal=z["normal"], color=z["color"])
+        Qg = pkg.make_points(z["queries"])
+        with pkg.Tree(Pg) as tree:
+            for k in z["ks"]:
+                k = int(k)
+                idx, d2 = tree.knn(Qg, k, radius=float(z["radius"]))
+                assert np.array_equal(idx, z[f"idx_k{k}"]), (name, k)
+                assert np.array_equal(d2, z[f"d2_k{k}"]), (name, k)
 
 
 def test_edge_cases(pkg, torch_cuda):
