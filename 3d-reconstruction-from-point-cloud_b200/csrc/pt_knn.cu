@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 #include "pt_knn_octet.cuh"
 #include "pt_knn_thread.cuh"
 #include "pt_knn_fkey.cuh"
+#include "pt_knn_scan.cuh"
 namespace pt {
 
 // Octet (variant 1) / thread (variant 2) kernel, then the warp kernel over the samples whose
@@ -368,7 +369,9 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
     uint32_t *count = (uint32_t *)ix->ws_ovf + (size_t)slot * ix->ovf_slot_words;
     uint32_t *list = count + 4;
     PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
-    if (variant == 4) {
+    if (variant == 5) {
+        PT_TRY(launch_scan<PT>(qp, count, list, s));
+    } else if (variant == 4) {
         PT_TRY(launch_fkey<PT>(qp, count, list, s));
     } else if (variant == 2) {
         PT_TRY(launch_thread<PT>(qp, count, list, s));
@@ -422,10 +425,11 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
     }
     int variant = opt_knn_variant();
     if (variant < 0) {
-        // auto: at k > 16 the fp32-keyed kernel's smaller entries keep far more warps resident
-        // (measured +21 % at cfg4's k = 32); at k <= 16 the thread kernel is as fast or faster
-        // on every workload shape -- DESIGN.md section 4
-        variant = qp.k > 16 ? 4 : 2;
+        // auto: the scan kernel (unsorted top-k slots, linear max scan) is 3-9 % ahead of the
+        // thread kernel at k <= 16 and 23 % at k = 32; radius-bounded searches with k <= 16 mostly
+        // end with short lists, where the thread kernel's exact entries win -- DESIGN.md section 4
+        const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
+        variant = (qp.k <= 16 && bounded) ? 2 : 5;
     }
     return ix->coord_f64 ? launch_with_fallback<PointD>(ix, qp, variant, s, slot)
                          : launch_with_fallback<PointF>(ix, qp, variant, s, slot);

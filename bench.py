@@ -365,7 +365,7 @@ def main():
 
     variant_used = pkg.get_option("knn_variant")
     if variant_used < 0:      # auto rule of launch_query (pt_knn.cu)
-        variant_used = 4 if k > 16 else 2
+        variant_used = 2 if (k <= 16 and w.radius is not None) else 5
     peak, peak_src = measured_peaks()
     alg_bytes = algorithmic_bytes_per_sample(k) * m
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
