@@ -12,7 +12,7 @@ namespace pt {
 
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_verbose{-1};
-static std::atomic<int> g_knn_variant{-1};  // -1 auto (default): scan or thread kernel; 5 scan, 4 fkey, 2 thread, 1 octet, 0 warp
+static std::atomic<int> g_knn_variant{-1};  // -1 auto (default): scan or thread kernel; 5 scan, 2 thread, 1 octet, 0 warp
 static std::atomic<int> g_sort{1};    // 1 hand-written radix sort (default), 0 cub::DeviceRadixSort
 static std::atomic<int> g_order{2};   // 0 Morton, 1 Hilbert, 2 Hilbert + kd refinement (default)
 

@@ -353,12 +353,11 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 }  // namespace pt
 #include "pt_knn_octet.cuh"
 #include "pt_knn_thread.cuh"
-#include "pt_knn_fkey.cuh"
 #include "pt_knn_scan.cuh"
 namespace pt {
 
-// Octet (variant 1) / thread (variant 2) kernel, then the warp kernel over the samples whose
-// private queue overflowed.  The overflow list lives in the index (grown on demand).
+// Scan (variant 5) / thread (variant 2) / octet (variant 1) kernel, then the warp kernel over the
+// samples that could not discharge their queue proof obligation.  The overflow list lives in the index (grown on demand).
 template <typename PT>
 static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s,
                                 int slot)
@@ -371,8 +370,6 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
     PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
     if (variant == 5) {
         PT_TRY(launch_scan<PT>(qp, count, list, s));
-    } else if (variant == 4) {
-        PT_TRY(launch_fkey<PT>(qp, count, list, s));
     } else if (variant == 2) {
         PT_TRY(launch_thread<PT>(qp, count, list, s));
     } else {

@@ -2,7 +2,7 @@
 import sys; sys.path.insert(0, "/root/repo")
 import torch, __graft_entry__ as ge
 pkg = ge.package(); torch.cuda.set_device(0); dev = torch.device("cuda", 0)
-variants = [int(a) for a in sys.argv[1:]] or [2, 4]
+variants = [int(a) for a in sys.argv[1:]] or [2, 5]
 GRIDS = (448, 896)
 w = pkg.synth.CONFIGS["cfg2"]; k = w.k
 pos, attrs = pkg.synth.cloud_device(w.n_points, w.seed)

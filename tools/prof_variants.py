@@ -1,4 +1,4 @@
-"""Two kernel variants against each other on a workload (default 2 vs 4 on cfg2): bit-equality of every output, timing,
+"""Two kernel variants against each other on a workload (default 2 vs 5 on cfg2): bit-equality of every output, timing,
 and (with a -DPT_STATS build) the work counters."""
 import sys; sys.path.insert(0, "/root/repo")
 import torch, __graft_entry__ as ge
@@ -11,7 +11,7 @@ q = pkg.synth.samples_device(w.gu, w.gv, center=w.center); m = q.shape[0]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 tree = pkg.DeviceTree(pos, attrs)
 res = {}
-variants = [int(a) for a in sys.argv[2:]] or [2, 4]
+variants = [int(a) for a in sys.argv[2:]] or [2, 5]
 for variant in variants:
     pkg.set_option("knn_variant", variant)
     idx = torch.full((m, k), -7, dtype=torch.int32, device=dev); rgba = torch.zeros((m, 4), dtype=torch.uint8, device=dev)
