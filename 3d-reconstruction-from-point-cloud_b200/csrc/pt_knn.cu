@@ -422,11 +422,12 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
     }
     int variant = opt_knn_variant();
     if (variant < 0) {
-        // auto: the scan kernel (unsorted top-k slots, linear max scan) is 3-9 % ahead of the
-        // thread kernel at k <= 16 and 23 % at k = 32; radius-bounded searches with k <= 16 mostly
-        // end with short lists, where the thread kernel's exact entries win -- DESIGN.md section 4
+        // auto (measured): the scan kernel is 3-9 % ahead of the thread
+        // kernel on launches that fill the GPU and 23 % at k = 32; on small launches (the ~25 k
+        // sample chunks of the host pipeline) and on radius-bounded searches, which mostly end
+        // with short lists, the thread kernel's exact entries win at k <= 16
         const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
-        variant = (qp.k <= 16 && bounded) ? 2 : 5;
+        variant = (qp.k > 16 || (!bounded && qp.m >= 100000u)) ? 5 : 2;
     }
     return ix->coord_f64 ? launch_with_fallback<PointD>(ix, qp, variant, s, slot)
                          : launch_with_fallback<PointF>(ix, qp, variant, s, slot);

@@ -58,9 +58,9 @@ def algorithmic_bytes_per_sample(k):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the query kernel from the
-# `ncu --set full` capture committed under profiles/ (r1_knn_thread_kernel_ncu_summary.txt):
+# `ncu --set full` captures committed under profiles/ (r1_knn_{scan,thread}_kernel_ncu_summary.txt):
 # valid only for the workload / kernel it was captured on.
-NCU_TRAFFIC = {("cfg2", 16, 2): 815.12e6 + 17.60e6}
+NCU_TRAFFIC = {("cfg2", 16, 5): 1000.76e6 + 17.30e6, ("cfg2", 16, 2): 815.12e6 + 17.60e6}
 
 
 def measured_peaks():
@@ -365,7 +365,7 @@ def main():
 
     variant_used = pkg.get_option("knn_variant")
     if variant_used < 0:      # auto rule of launch_query (pt_knn.cu)
-        variant_used = 2 if (k <= 16 and w.radius is not None) else 5
+        variant_used = 5 if (k > 16 or (w.radius is None and m >= 100000)) else 2
     peak, peak_src = measured_peaks()
     alg_bytes = algorithmic_bytes_per_sample(k) * m
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
@@ -391,7 +391,7 @@ def main():
                      "frac": achieved / peak,
                      "traffic": (NCU_TRAFFIC.get((args.workload, k, variant_used))
                                  if world == 1 and not (args.points or args.grid) else None),
-                     "traffic_source": "ncu --set full, profiles/r1_knn_thread_kernel_ncu_summary.txt",
+                     "traffic_source": "ncu --set full, profiles/r1_knn_scan_kernel_ncu_summary.txt",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel": "knn_*_kernel",
                      "kernel_ms": ms_per_step},

@@ -6,6 +6,8 @@ pkg = ge.package(); torch.cuda.set_device(0); dev = torch.device("cuda", 0)
 w = pkg.synth.CONFIGS["cfg2"]; k = w.k
 pos, attrs = pkg.synth.cloud_device(w.n_points, w.seed)
 q = pkg.synth.samples_device(w.gu, w.gv); m = q.shape[0]
+import os
+if os.environ.get("PT_VARIANT"): pkg.set_option("knn_variant", int(os.environ["PT_VARIANT"]))
 tree = pkg.DeviceTree(pos, attrs)
 q_host = pkg.synth.queries_to_host(q, pinned=True)
 qh = q_host.numpy().view(pkg.POINT_DTYPE).reshape(-1)
