@@ -20,6 +20,9 @@ namespace pt {
 constexpr int SCAN_SB = 5;                       // slot bits inside a key (k <= 32)
 constexpr uint32_t SCAN_SM = (1u << SCAN_SB) - 1u;
 
+#ifndef PT_SCAN_PREFETCH
+#define PT_SCAN_PREFETCH 1
+#endif
 #ifndef PT_SCAN_MIN_BLOCKS
 #define PT_SCAN_MIN_BLOCKS 20
 #endif
@@ -329,6 +332,11 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     // columns.
     double *hd = reinterpret_cast<double *>(t_smem) + tid;                                        // [k]
     int *hi = reinterpret_cast<int *>(t_smem + 8 * T_THREADS * (size_t)KP) + tid;                 // [k]
+#if PT_SCAN_PREFETCH
+    // the loop below waits for one point per step: start all the loads now
+    for (int j = 0; j < hn; ++j)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const PT *>(P.pts) + pis[j * T_THREADS]));
+#endif
     for (int j = k - 1; j >= 0; --j) {
         double d = 0.0;
         int pidx = 0;
