@@ -119,7 +119,9 @@ def test_reference_call_site_shape(pkg, pto, torch_cuda):
                 assert [g[1] for g in got] == ref_d2[v].tolist()
 
 
-def test_device_api_ids_and_radius_per_query(pkg, pto, torch_cuda):
+@pytest.mark.parametrize("variant", [5, 2])
+def test_device_api_ids_and_radius_per_query(variant, pkg, pto, torch_cuda):
+    pkg.set_option("knn_variant", variant)
     torch = torch_cuda
     rng = np.random.default_rng(21)
     n, m, k = 50_000, 2_000, 16
@@ -158,8 +160,10 @@ def test_device_api_ids_and_radius_per_query(pkg, pto, torch_cuda):
     tree.close()
 
 
+@pytest.mark.parametrize("variant", [5, 2])
 @pytest.mark.parametrize("n_slabs,k", [(2, 8), (3, 16), (8, 32)])
-def test_slab_merge_equals_single_index(n_slabs, k, pkg, pto, torch_cuda):
+def test_slab_merge_equals_single_index(n_slabs, k, variant, pkg, pto, torch_cuda):
+    pkg.set_option("knn_variant", variant)
     """SURVEY 8(e): R slabs on one GPU, per-slab top-k, merged by the K5 kernel, must be
     bit-identical to the single-index result."""
     torch = torch_cuda
@@ -252,7 +256,9 @@ def test_tiny_queue_stays_exact(cap, variant, pkg, pto, golden_dir, torch_cuda):
                 assert np.array_equal(d2, z[f"d2_k{k}"]), (name, k)
 
 
-def test_edge_cases(pkg, torch_cuda):
+@pytest.mark.parametrize("variant", [-1, 5, 2, 1, 0])
+def test_edge_cases(variant, pkg, torch_cuda):
+    pkg.set_option("knn_variant", variant)
     empty = np.zeros(0, dtype=pkg.POINT_DTYPE)
     Q = pkg.make_points(np.zeros((3, 3)))
     with pkg.Tree(empty) as t:                       # empty cloud
