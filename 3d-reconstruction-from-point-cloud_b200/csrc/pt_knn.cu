@@ -410,7 +410,22 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
         PT_CUDA(cudaGetLastError());
         return PT_OK;
     }
-    if (opt_knn_variant() == 0) {
+    int variant = opt_knn_variant();
+    if (variant < 0) {
+        // auto (measured):
+        //  * up to ~12 k samples a launch is one partial wave and pays a thread-kernel block's
+        //    full latency (0.23 ms at cfg2's cloud); the warp kernel -- 32 lanes per sample --
+        //    answers it in 0.14-0.19 ms (cfg1: 0.079 vs 0.136 ms);
+        //  * the scan kernel is 3-9 % ahead of the thread kernel on launches that fill the GPU
+        //    and 23 % at k = 32;
+        //  * on mid-size launches (the ~25 k sample chunks of the host pipeline), on
+        //    radius-bounded searches, which mostly end with short lists, and on slab indexes
+        //    with an id map the thread kernel's exact entries win at k <= 16.
+        const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
+        if (qp.m <= 12288u) variant = 0;
+        else variant = (qp.k > 16 || (!bounded && qp.m >= 100000u && qp.ids == nullptr)) ? 5 : 2;
+    }
+    if (variant == 0) {
         unsigned blocks = (qp.m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         if (ix->coord_f64)
             knn_warp_kernel<PointD><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(qp);
@@ -419,16 +434,6 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
         count_launch();
         PT_CUDA(cudaGetLastError());
         return PT_OK;
-    }
-    int variant = opt_knn_variant();
-    if (variant < 0) {
-        // auto (measured): the scan kernel is 3-9 % ahead of the thread
-        // kernel on launches that fill the GPU and 23 % at k = 32; on small launches (the ~25 k
-        // sample chunks of the host pipeline) and on radius-bounded searches, which mostly end
-        // with short lists, the thread kernel's exact entries win at k <= 16
-        // (and on slab indexes with an id map: 0.75 vs 0.80 ms per multi-GPU step)
-        const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
-        variant = (qp.k > 16 || (!bounded && qp.m >= 100000u && qp.ids == nullptr)) ? 5 : 2;
     }
     return ix->coord_f64 ? launch_with_fallback<PointD>(ix, qp, variant, s, slot)
                          : launch_with_fallback<PointF>(ix, qp, variant, s, slot);

@@ -365,7 +365,8 @@ def main():
 
     variant_used = pkg.get_option("knn_variant")
     if variant_used < 0:      # auto rule of launch_query (pt_knn.cu)
-        variant_used = 5 if (k > 16 or (w.radius is None and m >= 100000 and slab is None)) else 2
+        variant_used = 0 if m <= 12288 else (
+            5 if (k > 16 or (w.radius is None and m >= 100000 and slab is None)) else 2)
     peak, peak_src = measured_peaks()
     alg_bytes = algorithmic_bytes_per_sample(k) * m
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9

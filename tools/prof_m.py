@@ -3,7 +3,8 @@ import sys; sys.path.insert(0, "/root/repo")
 import torch, __graft_entry__ as ge
 pkg = ge.package(); torch.cuda.set_device(0); dev = torch.device("cuda", 0)
 variants = [int(a) for a in sys.argv[1:]] or [2, 5]
-GRIDS = (448, 896)
+import os
+GRIDS = tuple(int(g) for g in os.environ.get("PT_GRIDS", "448,896").split(","))
 w = pkg.synth.CONFIGS["cfg2"]; k = w.k
 pos, attrs = pkg.synth.cloud_device(w.n_points, w.seed)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
