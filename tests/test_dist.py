@@ -155,6 +155,13 @@ def _worker(rank, world, port, case, tmpdir):
         assert np.allclose(out["normal"].numpy(), ref_nrm, rtol=1e-5, atol=1e-7)
         if case.get("expect_path"):
             assert st.stats["path"] == case["expect_path"], st.stats
+        # host-buffer entry point (generic path on this CPU engine): same results
+        host = {"idx": torch.empty((len(own_q), k), dtype=torch.int32),
+                "rgba": torch.empty((len(own_q), 4), dtype=torch.uint8),
+                "normal": torch.empty((len(own_q), 3), dtype=torch.float32)}
+        st.transfer_host(torch.from_numpy(np.ascontiguousarray(V["ver"][own_q])), k, host, radius=radius)
+        for name in ("idx", "rgba", "normal"):
+            assert torch.equal(host[name], out[name]), f"rank {rank}: transfer_host {name}"
         stats = torch.tensor([st.stats["crossing"], len(own_q)], dtype=torch.int64)
         dist.all_reduce(stats)
         if rank == 0:
