@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 
 }  // namespace pt
 #include "pt_knn_octet.cuh"
+#include "pt_knn_traverse.cuh"
 #include "pt_knn_thread.cuh"
 #include "pt_knn_scan.cuh"
 namespace pt {

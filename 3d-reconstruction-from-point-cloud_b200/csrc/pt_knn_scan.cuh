@@ -55,106 +55,14 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         qz = __ldg(P.queries + 3 * (size_t)q + 2);
         r2 = P.r2_per_query ? __ldg(P.r2_per_query + q) : P.r2;
     }
-    const float qdn[3] = {__double2float_rd(qx), __double2float_rd(qy), __double2float_rd(qz)};
-    const float qup[3] = {__double2float_ru(qx), __double2float_ru(qy), __double2float_ru(qz)};
     const float bound_r = __double2float_ru(r2);
     float bound = bound_r;
 
     int hn = 0;                      // slots in use
     uint32_t rtk = 0xffffffffu;      // truncated key (key >> 5) of the current k-th candidate ...
     int rslot = 0;                   // ... and its slot -- meaningful once hn == k
-    int pq_n = 0;
-    uint32_t lost = 0xffffffffu;   // smallest key of a queue entry that had to be given up
-    const int qcap = min(max(P.pq_cap, 2), TPQ_CAP);   // runtime cap <= layout (tests shrink it)
+    Traverser<PT, T_THREADS> tr(P, pqk, pqw, qx, qy, qz, !done);
 
-    // drop the queue entries that lie beyond the bound (it only shrinks, so they are dead) and
-    // rebuild the heap in place
-    auto pq_compact = [&]() {
-        int live = 0;
-        for (int e = 0; e < pq_n; ++e) {
-            const uint32_t ek = pqk[e * T_THREADS], ew = pqw[e * T_THREADS];
-            if (__uint_as_float(ek & ~0xfu) <= bound) {
-                int i = live++;
-                while (i > 0) {
-                    int p = (i - 1) >> 1;
-                    uint32_t pk = pqk[p * T_THREADS];
-                    if (pk <= ek) break;
-                    pqk[i * T_THREADS] = pk;
-                    pqw[i * T_THREADS] = pqw[p * T_THREADS];
-                    i = p;
-                }
-                pqk[i * T_THREADS] = ek;
-                pqw[i * T_THREADS] = ew;
-            }
-        }
-        pq_n = live;
-    };
-    auto pq_push = [&](uint32_t key, uint32_t word) {
-        if (pq_n == qcap) {
-            pq_compact();
-            if (pq_n == qcap) {
-                // still full of live entries: give up the least promising one (the largest key;
-                // in a min-heap it is among the leaves).  Exactness is kept by remembering the
-                // smallest key ever given up: if the final bound stays below it, no dropped
-                // subtree could have held a neighbour; otherwise the sample takes the fallback.
-                int mi = qcap / 2;
-                uint32_t mk = pqk[mi * T_THREADS];
-#pragma unroll 1
-                for (int e = qcap / 2 + 1; e < qcap; ++e) {
-                    const uint32_t ek = pqk[e * T_THREADS];
-                    if (ek > mk) { mk = ek; mi = e; }
-                }
-                if (key >= mk) { lost = min(lost, key); return; }
-                lost = min(lost, mk);
-                int i = mi;
-                while (i > 0) {
-                    int p = (i - 1) >> 1;
-                    uint32_t pk = pqk[p * T_THREADS];
-                    if (pk <= key) break;
-                    pqk[i * T_THREADS] = pk;
-                    pqw[i * T_THREADS] = pqw[p * T_THREADS];
-                    i = p;
-                }
-                pqk[i * T_THREADS] = key;
-                pqw[i * T_THREADS] = word;
-                return;
-            }
-        }
-        int i = pq_n++;
-        while (i > 0) {
-            int p = (i - 1) >> 1;
-            uint32_t pk = pqk[p * T_THREADS];
-            if (pk <= key) break;
-            pqk[i * T_THREADS] = pk;
-            pqw[i * T_THREADS] = pqw[p * T_THREADS];
-            i = p;
-        }
-        pqk[i * T_THREADS] = key;
-        pqw[i * T_THREADS] = word;
-    };
-    auto pq_pop = [&](uint32_t &key, uint32_t &word) {
-        key = pqk[0];
-        word = pqw[0];
-        const int n = --pq_n;
-        if (n == 0) return;
-        const uint32_t lk = pqk[n * T_THREADS], lw = pqw[n * T_THREADS];
-        int i = 0;
-        for (;;) {
-            int c = 2 * i + 1;
-            if (c >= n) break;
-            uint32_t ck = pqk[c * T_THREADS];
-            if (c + 1 < n) {
-                uint32_t ck2 = pqk[(c + 1) * T_THREADS];
-                if (ck2 < ck) { ck = ck2; ++c; }
-            }
-            if (ck >= lk) break;
-            pqk[i * T_THREADS] = ck;
-            pqw[i * T_THREADS] = pqw[c * T_THREADS];
-            i = c;
-        }
-        pqk[i * T_THREADS] = lk;
-        pqw[i * T_THREADS] = lw;
-    };
     // exact (d2, index) of an entry, re-read from the sorted cloud (rare: only on equal keys)
     auto exact_of = [&](uint32_t pos, double &d, int &idx) {
         double px, py, pz;
@@ -191,66 +99,8 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         pis[slot * T_THREADS] = (uint32_t)e;
     };
 
-    bool cur_valid = !done;
-    int cur_tl = P.t_levels;
-    uint32_t cur_id = 0, cur_mask = 0xffu;
-
     for (;;) {
-        int leaf = -1;
-        while (!done && leaf < 0) {
-            if (!cur_valid) {
-                if (pq_n == 0) { done = true; break; }
-                uint32_t key, word;
-                pq_pop(key, word);
-                if (__uint_as_float(key & ~0xfu) > bound) { done = true; break; }  // rest is farther
-                cur_tl = (int)(key & 0xfu);
-                cur_id = word & 0x7fffffu;
-                cur_mask = word >> 23;
-            }
-            cur_valid = false;
-            const int pl = (cur_tl - 1) * T_LOG;
-            const uint32_t cnt = P.pyr.count[pl];
-            const Box *boxes = P.pyr.level[pl];
-            float best = INFINITY, second = INFINITY;
-            int best_c = -1;
-            uint32_t rem = 0;
-            Box cb[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) cb[c] = load_box(boxes + min(cur_id * 8 + c, cnt - 1));
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (((cur_mask >> c) & 1u) && cur_id * 8 + c < cnt) {
-                    const float lb = box_lower_bound(qdn, qup, cb[c]);
-                    if (lb <= bound) {
-                        rem |= 1u << c;
-                        if (lb < best) { second = best; best = lb; best_c = c; }
-                        else second = fminf(second, lb);
-                    }
-                }
-            }
-            if (best_c < 0) continue;
-            rem &= ~(1u << best_c);
-            if (rem) pq_push((__float_as_uint(second) & ~0xfu) | (uint32_t)cur_tl, (rem << 23) | cur_id);
-            const uint32_t child = cur_id * 8 + (uint32_t)best_c;
-            if (cur_tl == 1) {
-                leaf = (int)child;
-#if PT_T_PREFETCH
-                {
-                    const char *lp = reinterpret_cast<const char *>(P.pts) + (size_t)child * LEAF * sizeof(PT);
-#pragma unroll
-                    for (int l = 0; l < (int)(LEAF * sizeof(PT) / 128); ++l)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + 128 * l));
-                }
-#endif
-            } else {
-                const bool dive = hn < k || pq_n == 0 ||
-                                  best <= __uint_as_float(pqk[0] & ~0xfu);
-                if (dive) { cur_valid = true; cur_tl -= 1; cur_id = child; cur_mask = 0xffu; }
-                else pq_push((__float_as_uint(best) & ~0xfu) | (uint32_t)(cur_tl - 1),
-                             (0xffu << 23) | child);
-            }
-            if (overflow) { done = true; leaf = -1; }
-        }
+        const int leaf = tr.next_leaf(bound, hn < k, done);
         if (__all_sync(0xffffffffu, done)) break;
 
         // ---- leaf phase: every lane that holds a leaf scans it, 8 points per chunk -------------
@@ -296,7 +146,6 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
                     }
                 }
             }
-            if (overflow) { done = true; leaf = -1; }
         }
         // smallest fp32 value that is certainly > the k-th exact d2 (its key is truncated)
         if (hn == k) {
@@ -304,12 +153,11 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
             bound = fminf(__uint_as_float((rtk + 1u) << SCAN_SB), bound_r);
             // the siblings queued during the first dive were pushed with an infinite bound:
             // most of them are dead now, which keeps a small queue sufficient
-            if (first && bound < bound_r) pq_compact();
+            if (first && bound < bound_r) tr.compact(bound);
         }
     }
 
-    // a dropped queue entry matters only if its subtree could still reach inside the final bound
-    if (lost != 0xffffffffu && __uint_as_float(lost & ~0xfu) <= bound) overflow = true;
+    overflow = tr.proof_failed(bound);
 #ifdef PT_STATS
     {
         unsigned v = (q < P.m && overflow) ? 1u : 0u, w = q < P.m ? 1u : 0u;

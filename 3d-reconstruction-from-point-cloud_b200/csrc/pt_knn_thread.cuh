@@ -16,38 +16,13 @@
 
 namespace pt {
 
-// -DPT_STATS: per-launch work counters (diagnosis builds only; pt_debug_stats reads them)
-#ifdef PT_STATS
-__device__ unsigned long long g_stats[16];
-#define PT_STAT(slot, v) (st_[slot] += (v))
-#else
-#define PT_STAT(slot, v) ((void)0)
-#endif
-// slots: 0 expansions, 1 leaves, 2 pushes, 3 pops, 4 compactions, 5 heap inserts, 6 candidates
-// parked, 7 warp rounds, 8 overflowed samples, 9 samples, 10 drain iterations (warp), 11 expand
-// iterations (warp)
-
 #ifndef PT_T_THREADS
 #define PT_T_THREADS 32      // one warp per block: finest scheduling granularity (sweep: 32 > 64 > 128)
 #endif
 #ifndef PT_T_CHUNK
 #define PT_T_CHUNK 8          // leaf points scanned between two drains (= pending capacity)
 #endif
-#ifndef PT_T_PREFETCH
-#define PT_T_PREFETCH 1       // L2-prefetch the chosen leaf while other lanes still traverse
-#endif
 constexpr int T_THREADS = PT_T_THREADS;
-constexpr int T_LOG = 3;
-#ifndef PT_TPQ_CAP
-// queue entries per sample.  A full queue gives up its least promising entry (see pq_push), so a
-// small queue is exact and cheap: 8 already works (a few fallbacks per million samples), 12 had
-// none on any workload shape, and every 8 entries less is one more resident warp per SM
-#define PT_TPQ_CAP 12
-#endif
-#ifndef PT_T_BATCH_BOXES
-#define PT_T_BATCH_BOXES 1
-#endif
-constexpr int TPQ_CAP = PT_TPQ_CAP;
 constexpr int TPD_CAP = PT_T_CHUNK;
 
 // sift `(cd, ci)` down from `pos` in the max-heap column of size n (element j at [j * STRIDE])
@@ -172,8 +147,6 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         qz = __ldg(P.queries + 3 * (size_t)q + 2);
         r2 = P.r2_per_query ? __ldg(P.r2_per_query + q) : P.r2;
     }
-    const float qdn[3] = {__double2float_rd(qx), __double2float_rd(qy), __double2float_rd(qz)};
-    const float qup[3] = {__double2float_ru(qx), __double2float_ru(qy), __double2float_ru(qz)};
     float bound = __double2float_ru(r2);
 
 #ifdef PT_STATS
@@ -183,174 +156,13 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     int hn = 0;                 // candidates held; the column is a max-heap once hn == k
     double root_d = INFINITY;   // heap root (current k-th) -- meaningful once hn == k
     int root_i = IDX_NONE;
-    int pq_n = 0;
-    uint32_t lost = 0xffffffffu;   // smallest key of a queue entry that had to be given up
-    const int qcap = min(max(P.pq_cap, 2), TPQ_CAP);   // runtime cap <= layout (tests shrink it)
-
-    // queue entry: key = bound bits with the low 4 mantissa bits replaced by the node's t-level
-    // (still a valid, slightly smaller lower bound); word = unvisited-children mask << 23 | id
-    auto pq_push = [&](uint32_t key, uint32_t word) {
-        PT_STAT(2, 1);
-        if (pq_n == qcap) {
-            PT_STAT(4, 1);
-            // full: the bound only decreases, so entries above it are dead -- drop them and
-            // rebuild the heap (rare); only a queue full of live entries is an overflow
-            int live = 0;
-#pragma unroll 1
-            for (int e = 0; e < qcap; ++e) {
-                const uint32_t ek = pqk[e * T_THREADS], ew = pqw[e * T_THREADS];
-                if (__uint_as_float(ek & ~0xfu) <= bound) {
-                    int i = live++;
-                    while (i > 0) {
-                        int p = (i - 1) >> 1;
-                        uint32_t pk = pqk[p * T_THREADS];
-                        if (pk <= ek) break;
-                        pqk[i * T_THREADS] = pk;
-                        pqw[i * T_THREADS] = pqw[p * T_THREADS];
-                        i = p;
-                    }
-                    pqk[i * T_THREADS] = ek;
-                    pqw[i * T_THREADS] = ew;
-                }
-            }
-            pq_n = live;
-            if (pq_n == qcap) {
-                // still full of live entries: give up the least promising one (the largest key;
-                // in a min-heap it is among the leaves).  Exactness is kept by remembering the
-                // smallest key ever given up: if the final bound stays below it, no dropped
-                // subtree could have held a neighbour; otherwise the sample takes the fallback.
-                int mi = qcap / 2;
-                uint32_t mk = pqk[mi * T_THREADS];
-#pragma unroll 1
-                for (int e = qcap / 2 + 1; e < qcap; ++e) {
-                    const uint32_t ek = pqk[e * T_THREADS];
-                    if (ek > mk) { mk = ek; mi = e; }
-                }
-                if (key >= mk) { lost = min(lost, key); return; }
-                lost = min(lost, mk);
-                int i = mi;
-                while (i > 0) {
-                    int p = (i - 1) >> 1;
-                    uint32_t pk = pqk[p * T_THREADS];
-                    if (pk <= key) break;
-                    pqk[i * T_THREADS] = pk;
-                    pqw[i * T_THREADS] = pqw[p * T_THREADS];
-                    i = p;
-                }
-                pqk[i * T_THREADS] = key;
-                pqw[i * T_THREADS] = word;
-                return;
-            }
-        }
-        int i = pq_n++;
-        while (i > 0) {
-            int p = (i - 1) >> 1;
-            uint32_t pk = pqk[p * T_THREADS];
-            if (pk <= key) break;
-            pqk[i * T_THREADS] = pk;
-            pqw[i * T_THREADS] = pqw[p * T_THREADS];
-            i = p;
-        }
-        pqk[i * T_THREADS] = key;
-        pqw[i * T_THREADS] = word;
-    };
-    auto pq_pop = [&](uint32_t &key, uint32_t &word) {
-        key = pqk[0];
-        word = pqw[0];
-        const int n = --pq_n;
-        if (n == 0) return;
-        const uint32_t lk = pqk[n * T_THREADS], lw = pqw[n * T_THREADS];
-        int i = 0;
-        for (;;) {
-            int c = 2 * i + 1;
-            if (c >= n) break;
-            uint32_t ck = pqk[c * T_THREADS];
-            if (c + 1 < n) {
-                uint32_t ck2 = pqk[(c + 1) * T_THREADS];
-                if (ck2 < ck) { ck = ck2; ++c; }
-            }
-            if (ck >= lk) break;
-            pqk[i * T_THREADS] = ck;
-            pqw[i * T_THREADS] = pqw[c * T_THREADS];
-            i = c;
-        }
-        pqk[i * T_THREADS] = lk;
-        pqw[i * T_THREADS] = lw;
-    };
-
-    // the node being expanded (not in the queue)
-    bool cur_valid = !done;
-    int cur_tl = P.t_levels;
-    uint32_t cur_id = 0, cur_mask = 0xffu;
+    Traverser<PT, T_THREADS> tr(P, pqk, pqw, qx, qy, qz, !done);
+#ifdef PT_STATS
+    tr.st_ = st_;
+#endif
 
     for (;;) {
-        int leaf = -1;
-        while (!done && leaf < 0) {
-            if (!cur_valid) {
-                if (pq_n == 0) { done = true; break; }
-                uint32_t key, word;
-                pq_pop(key, word);
-                PT_STAT(3, 1);
-                if (__uint_as_float(key & ~0xfu) > bound) { done = true; break; }  // rest is farther
-                cur_tl = (int)(key & 0xfu);
-                cur_id = word & 0x7fffffu;
-                cur_mask = word >> 23;
-            }
-            cur_valid = false;
-            PT_STAT(0, 1);
-            if (tid == (unsigned)(__ffs(__activemask()) - 1)) PT_STAT(11, 1);
-            // expand: test the unvisited children (t-level cur_tl - 1)
-            const int pl = (cur_tl - 1) * T_LOG;
-            const uint32_t cnt = P.pyr.count[pl];
-            const Box *boxes = P.pyr.level[pl];
-            float best = INFINITY, second = INFINITY;
-            int best_c = -1;
-            uint32_t rem = 0;
-            // all 8 child boxes are fetched up front (16 independent 16-byte loads in flight);
-            // children past the end of the level are clamped and masked out below
-#if PT_T_BATCH_BOXES
-            Box cb[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) cb[c] = load_box(boxes + min(cur_id * 8 + c, cnt - 1));
-#endif
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (((cur_mask >> c) & 1u) && cur_id * 8 + c < cnt) {
-#if PT_T_BATCH_BOXES
-                    const float lb = box_lower_bound(qdn, qup, cb[c]);
-#else
-                    const float lb = box_lower_bound(qdn, qup, load_box(boxes + cur_id * 8 + c));
-#endif
-                    if (lb <= bound) {
-                        rem |= 1u << c;
-                        if (lb < best) { second = best; best = lb; best_c = c; }
-                        else second = fminf(second, lb);
-                    }
-                }
-            }
-            if (best_c < 0) continue;
-            rem &= ~(1u << best_c);
-            if (rem) pq_push((__float_as_uint(second) & ~0xfu) | (uint32_t)cur_tl, (rem << 23) | cur_id);
-            const uint32_t child = cur_id * 8 + (uint32_t)best_c;
-            if (cur_tl == 1) {
-                leaf = (int)child;
-#if PT_T_PREFETCH
-                {
-                    const char *lp = reinterpret_cast<const char *>(P.pts) + (size_t)child * LEAF * sizeof(PT);
-#pragma unroll
-                    for (int l = 0; l < (int)(LEAF * sizeof(PT) / 128); ++l)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + 128 * l));
-                }
-#endif
-            } else {
-                const bool dive = hn < k || pq_n == 0 ||
-                                  best <= __uint_as_float(pqk[0] & ~0xfu);
-                if (dive) { cur_valid = true; cur_tl -= 1; cur_id = child; cur_mask = 0xffu; }
-                else pq_push((__float_as_uint(best) & ~0xfu) | (uint32_t)(cur_tl - 1),
-                             (0xffu << 23) | child);
-            }
-            if (overflow) { done = true; leaf = -1; }
-        }
+        const int leaf = tr.next_leaf(bound, hn < k, done);
         if (__all_sync(0xffffffffu, done)) break;
 
         // ---- leaf phase: every lane that holds a leaf scans it, 8 points per chunk -------------
@@ -402,8 +214,7 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         if (hn == k) bound = __double2float_ru(fmin(root_d, r2));
     }
 
-    // a dropped queue entry matters only if its subtree could still reach inside the final bound
-    if (lost != 0xffffffffu && __uint_as_float(lost & ~0xfu) <= bound) overflow = true;
+    overflow = tr.proof_failed(bound);
 #ifdef PT_STATS
     st_[8] = overflow ? 1 : 0;
     st_[9] = q < P.m ? 1 : 0;
