@@ -12,7 +12,7 @@ namespace pt {
 
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_verbose{-1};
-static std::atomic<int> g_knn_variant{-1};  // -1 auto (default): scan or thread kernel; 5 scan, 2 thread, 1 octet, 0 warp
+static std::atomic<int> g_knn_variant{-1};  // -1 auto (default): scan or thread kernel; 5 scan, 2 thread, 0 warp
 static std::atomic<int> g_sort{1};    // 1 hand-written radix sort (default), 0 cub::DeviceRadixSort
 static std::atomic<int> g_order{2};   // 0 Morton, 1 Hilbert, 2 Hilbert + kd refinement (default)
 
@@ -52,7 +52,11 @@ int opt_smem_pad() { return g_smem_pad.load(); }
 int set_option(const char *name, int value)
 {
     if (!name) return PT_ERR_INVALID_ARG;
-    if (!strcmp(name, "knn_variant")) { g_knn_variant.store(value); return PT_OK; }
+    if (!strcmp(name, "knn_variant")) {
+        if (value != -1 && value != 0 && value != 2 && value != 5) return PT_ERR_INVALID_ARG;
+        g_knn_variant.store(value);
+        return PT_OK;
+    }
     if (!strcmp(name, "order")) { g_order.store(value); return PT_OK; }
     if (!strcmp(name, "sort")) { g_sort.store(value); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }

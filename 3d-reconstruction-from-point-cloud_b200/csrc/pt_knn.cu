@@ -3,12 +3,13 @@
 // metric src/Distance.h:6-11, pruning bound src/Distance.h:27-57).
 //
 // Three kernels share the helpers in this file:
-//   variant 2 ("thread", pt_knn_thread.cuh): one thread per sample, state in shared-memory columns;
-//   variant 1 ("octet",  pt_knn_octet.cuh) : eight lanes per sample, coalesced 8-wide box tests;
+//   variant 5 ("scan",   pt_knn_scan.cuh)  : one thread per sample, unsorted top-k slots;
+//   variant 2 ("thread", pt_knn_thread.cuh): one thread per sample, top-k heap;
+//     both walk the box pyramid with pt_knn_traverse.cuh, state in shared-memory columns;
 //   variant 0 ("warp",   below)            : one warp per sample, 32-wide levels, nearest-child-
-//     first DFS, top-k as a sorted list distributed one entry per lane.  Slowest (instruction
-//     bound on the serial list insertions) but has no per-sample state limits: it re-runs the
-//     samples whose private queue overflowed in the other two (exact fallback).
+//     first DFS, top-k as a sorted list distributed one entry per lane.  Most instructions per
+//     sample but the shortest latency and no per-sample state limits: it answers small launches
+//     and re-runs the samples the other two hand over (exact fallback).
 #include "pt_index.cuh"
 
 namespace pt {
@@ -351,14 +352,13 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 }
 
 }  // namespace pt
-#include "pt_knn_octet.cuh"
 #include "pt_knn_traverse.cuh"
 #include "pt_knn_thread.cuh"
 #include "pt_knn_scan.cuh"
 namespace pt {
 
-// Scan (variant 5) / thread (variant 2) / octet (variant 1) kernel, then the warp kernel over the
-// samples that could not discharge their queue proof obligation.  The overflow list lives in the index (grown on demand).
+// Scan (variant 5) / thread (variant 2) kernel, then the warp kernel over the samples that could
+// not discharge their queue proof obligation.  The overflow list lives in the index (grown on demand).
 template <typename PT>
 static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s,
                                 int slot)
@@ -371,10 +371,8 @@ static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant
     PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
     if (variant == 5) {
         PT_TRY(launch_scan<PT>(qp, count, list, s));
-    } else if (variant == 2) {
-        PT_TRY(launch_thread<PT>(qp, count, list, s));
     } else {
-        PT_TRY(launch_octet<PT>(qp, count, list, s));
+        PT_TRY(launch_thread<PT>(qp, count, list, s));
     }
     knn_warp_list_kernel<PT><<<148 * 4, WARPS_PER_BLOCK * 32, 0, s>>>(qp, count, list);
     count_launch();

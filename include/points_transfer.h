@@ -193,7 +193,7 @@ int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, 
 
 /* Tuning / introspection. */
 /* Options: "knn_variant" (-1 auto [default], 5 scan kernel, 2 thread kernel,
- * 1 octet, 0 warp), "order" (0 Morton, 1 Hilbert, 2 Hilbert + kd refinement [default]),
+ * 0 warp kernel), "order" (0 Morton, 1 Hilbert, 2 Hilbert + kd refinement [default]),
  * "sort" (1 hand-written radix sort [default], 0 cub), "host_chunks" (pipeline chunks of the
  * host-buffer API, default 8), "queue_cap" (tests: per-sample traversal queue entries, at most
  * the compiled 12), "verbose", "smem_pad" (diagnosis). */

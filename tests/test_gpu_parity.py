@@ -38,8 +38,8 @@ def _default_options(pkg):
     pkg.set_option("order", 2)
 
 
-# (knn_variant, order): thread kernel + Hilbert (default), octet kernel, warp kernel, Morton order
-MODES = [(2, 1), (1, 1), (0, 1), (2, 0), (2, 2), (0, 2), (1, 2), (5, 2), (5, 0)]   # order 2 = Hilbert + kd refinement
+# (knn_variant, order): thread / warp / scan kernel x Morton, Hilbert, Hilbert + kd refinement
+MODES = [(2, 1), (0, 1), (5, 1), (2, 0), (2, 2), (0, 2), (5, 2), (5, 0)]   # order 2 = Hilbert + kd refinement
 
 
 @pytest.mark.parametrize("mode", MODES, ids=lambda m: f"variant{m[0]}-order{m[1]}")
@@ -85,7 +85,7 @@ def test_f64_storage_forced_and_f32_rejected(pkg, pto, torch_cuda):
         assert np.array_equal(idx, ref_idx) and np.array_equal(d2, ref_d2)
 
 
-@pytest.mark.parametrize("variant", [5, 2, 1, 0])
+@pytest.mark.parametrize("variant", [5, 2, 0])
 @pytest.mark.parametrize("k", [1, 8, 16, 20, 32])
 def test_surface_cloud_vs_kdtree_oracle(k, variant, pkg, pto, torch_cuda):
     pkg.set_option("knn_variant", variant)
@@ -256,7 +256,7 @@ def test_tiny_queue_stays_exact(cap, variant, pkg, pto, golden_dir, torch_cuda):
                 assert np.array_equal(d2, z[f"d2_k{k}"]), (name, k)
 
 
-@pytest.mark.parametrize("variant", [-1, 5, 2, 1, 0])
+@pytest.mark.parametrize("variant", [-1, 5, 2, 0])
 def test_edge_cases(variant, pkg, torch_cuda):
     pkg.set_option("knn_variant", variant)
     empty = np.zeros(0, dtype=pkg.POINT_DTYPE)
