@@ -60,7 +60,7 @@ def algorithmic_bytes_per_sample(k):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the query kernel from the
 # `ncu --set full` captures committed under profiles/ (r1_knn_{scan,thread}_kernel_ncu_summary.txt):
 # valid only for the workload / kernel it was captured on.
-NCU_TRAFFIC = {("cfg2", 16, 5): 1000.76e6 + 17.30e6, ("cfg2", 16, 2): 815.12e6 + 17.60e6}
+NCU_TRAFFIC = {("cfg2", 16, 5): 1011.36e6 + 16.67e6, ("cfg2", 16, 2): 813.81e6 + 18.40e6}
 
 
 def measured_peaks():
