@@ -213,15 +213,12 @@ static inline size_t scan_kernel_smem(int k)
 template <typename PT>
 static int launch_scan(const QueryParams &qp, uint32_t *count, uint32_t *list, cudaStream_t s)
 {
-    static bool attr_set[2] = {false, false};
-    const int which = sizeof(PT) == 32;
-    if (!attr_set[which]) {
+    const size_t smem = scan_kernel_smem(qp.k) + (size_t)opt_smem_pad();
+    if (smem > 48 * 1024)   // only the occupancy probe (smem_pad) ever exceeds the default limit
         PT_CUDA(cudaFuncSetAttribute(knn_scan_kernel<PT>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set[which] = true;
-    }
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned blocks = (qp.m + T_THREADS - 1) / T_THREADS;
-    knn_scan_kernel<PT><<<blocks, T_THREADS, scan_kernel_smem(qp.k) + (size_t)opt_smem_pad(), s>>>(qp, count, list);
+    knn_scan_kernel<PT><<<blocks, T_THREADS, smem, s>>>(qp, count, list);
     count_launch();
     PT_CUDA(cudaGetLastError());
     return PT_OK;
