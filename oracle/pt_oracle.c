@@ -1,6 +1,8 @@
 /*
  * pt_oracle.c -- CPU oracle (test infrastructure, see pt_oracle.h header).
- * PARITY UNPINNED (no reference golden vectors exist; CGAL absent).
+ * Metric / box bound / record layout: pinned bit for bit on the reference's own headers
+ * (oracle/ref_shim.cpp -> oracle/_ref, tests/test_oracle.py).  Neighbour SEARCH: parity
+ * unpinned (no reference golden vectors exist; CGAL absent).
  *
  * Build: see oracle/Makefile.  Compiled like the reference's Release build
  * (src/CMakeLists.txt:7-9: -O3, no -march, no -ffast-math), plus

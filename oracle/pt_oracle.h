@@ -6,11 +6,15 @@
  * cpu_baseline / --impl reference legs may load this library, and only as the
  * checker (or as the timed CPU baseline), never as a fallback.
  *
- * PARITY UNPINNED: the reference (horizon-research/3D-Reconstruction-From-
- * Point-Cloud) ships no tests, golden vectors or fixtures, and its k-NN lives
- * in CGAL Spatial_searching (find_package(CGAL), version not pinned,
- * src/CMakeLists.txt:12), which is absent from this image, so the reference
- * cannot be compiled or run here.  This file restates
+ * PARITY OF THE SEARCH UNPINNED: the reference (horizon-research/3D-
+ * Reconstruction-From-Point-Cloud) ships no tests, golden vectors or fixtures,
+ * and its k-NN lives in CGAL Spatial_searching (find_package(CGAL), version
+ * not pinned, src/CMakeLists.txt:12), which is absent from this image, so the
+ * reference tool cannot be compiled or run here.  PINNED on the reference's
+ * own headers (src/Point.h + src/Distance.h compiled by `make ref`,
+ * ref_shim.cpp -> _ref/libref_metric.so; tests/test_oracle.py): the metric,
+ * the box bound, new_distance, the radius transform and the record layout,
+ * all bit for bit.  This file restates
  *   - the metric           src/Distance.h:6-11   (op order, fp64, no FMA)
  *   - the box lower bound  src/Distance.h:27-57
  *   - the incremental bound src/Distance.h:92-95

@@ -2,7 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY -- see oracle/pt_oracle.h.  Imported by tests/,
 ``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference``
-legs; never by the product package.  PARITY UNPINNED (no reference goldens).
+legs; never by the product package.  The neighbour SEARCH is parity-unpinned (no reference
+goldens, CGAL absent); the metric, the box bound and the record layout are pinned on the
+reference's own headers through ``ref_metric()`` (oracle/ref_shim.cpp -> oracle/_ref/).
 """
 import ctypes
 import os
@@ -30,6 +32,37 @@ def build(force=False):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
                        stdout=subprocess.DEVNULL)
     return _LIB_PATH
+
+
+_REF_PATH = os.path.join(_HERE, "_ref", "libref_metric.so")
+_ref = None
+
+
+def ref_metric():
+    """The reference's OWN src/Point.h + src/Distance.h compiled by `make -C oracle ref`
+    (oracle/ref_shim.cpp), or None where it was never built (/root/reference absent)."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF_PATH):
+            if os.path.exists("/root/reference/src/Distance.h"):
+                subprocess.run(["make", "-C", _HERE, "-s", "ref"], check=True, stdout=subprocess.DEVNULL)
+            else:
+                return None
+        R = ctypes.CDLL(_REF_PATH)
+        vp, dbl = ctypes.c_void_p, ctypes.c_double
+        R.ref_point_layout.argtypes = [vp]
+        R.ref_transformed_distance.restype = dbl
+        R.ref_transformed_distance.argtypes = [vp, vp]
+        R.ref_min_distance_to_rectangle.restype = dbl
+        R.ref_min_distance_to_rectangle.argtypes = [vp, vp, vp, vp]
+        R.ref_new_distance.restype = dbl
+        R.ref_new_distance.argtypes = [dbl, dbl, dbl]
+        R.ref_transformed_radius.restype = dbl
+        R.ref_transformed_radius.argtypes = [dbl]
+        R.ref_inverse_of_transformed_distance.restype = dbl
+        R.ref_inverse_of_transformed_distance.argtypes = [dbl]
+        _ref = R
+    return _ref
 
 
 _lib = None

@@ -101,6 +101,27 @@ def test_surface_cloud_vs_kdtree_oracle(k, variant, pkg, pto, torch_cuda):
     _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
 
 
+def test_gpu_d2_is_the_reference_metric(pkg, pto, torch_cuda):
+    """Every squared distance the CUDA path returns equals, bit for bit, what the reference's own
+    Distance::transformed_distance (src/Distance.h:6-11, compiled into oracle/_ref from the
+    reference's header) computes for that (sample, neighbour) pair."""
+    R = pto.ref_metric()
+    if R is None:
+        pytest.skip("oracle/_ref was never built (/root/reference absent at build time)")
+    P = pkg.synth.cloud_host(100_000, seed=3, side=50.0)
+    V = pkg.synth.samples_host(40, side=50.0)
+    for variant in (5, 2, 0):
+        pkg.set_option("knn_variant", variant)
+        with pkg.Tree(P) as tree:
+            idx, d2 = tree.knn(V, 16)
+        assert (idx >= 0).all()
+        for qi in range(0, len(V), 7):
+            for j in range(16):
+                ref = R.ref_transformed_distance(V[qi:qi + 1].ctypes.data,
+                                                 P[idx[qi, j]:idx[qi, j] + 1].ctypes.data)
+                assert d2[qi, j] == ref, (variant, qi, j)
+
+
 def test_reference_call_site_shape(pkg, pto, torch_cuda):
     # src/pointsTransfer.cpp:470-479: per face, per corner, K=20 search; iterate (point, d2)
     P = pkg.synth.cloud_host(20_000, seed=9, side=20.0)

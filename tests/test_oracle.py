@@ -6,6 +6,8 @@ src/Distance.h and CGAL's published k-d tree search (parity unpinned, see oracle
 import glob
 import os
 
+import ctypes
+
 import numpy as np
 import pytest
 from scipy.spatial import cKDTree
@@ -123,3 +125,73 @@ def test_reference_face_loop(pkg, pto):
     F = pkg.synth.grid_faces(12, 12)
     tree = pto.KdTree(P)
     assert tree.reference_face_loop(V, F, 20) == 3 * 20 * F.shape[0]
+
+
+# ---- pinned on the reference's own headers (oracle/_ref, built by `make -C oracle ref`) ----------
+def _ref_or_skip(pto):
+    R = pto.ref_metric()
+    if R is None:
+        pytest.skip("oracle/_ref was never built (/root/reference absent)")
+    return R
+
+
+def _rand_points(pto, n, rng, scale):
+    P = np.zeros(n, dtype=pto.POINT_DTYPE)
+    P["ver"] = (rng.standard_normal((n, 3)) * scale)
+    return P
+
+
+def test_record_layout_matches_reference_struct(pto):
+    """sizeof(Point) and the field offsets of the reference's src/Point.h, as its compiler lays
+    them out, are what the C ABI (PT_POINT_STRIDE), the oracle and the Python dtypes assume."""
+    R = _ref_or_skip(pto)
+    out = (ctypes.c_int * 6)()
+    R.ref_point_layout(out)
+    f = pto.POINT_DTYPE.fields
+    assert list(out) == [pto.POINT_DTYPE.itemsize, f["ver"][1], f["normal"][1], f["color"][1],
+                         f["U"][1], f["V"][1]] == [80, 0, 24, 48, 64, 72]
+
+
+def test_metric_is_bit_identical_to_reference_distance_h(pto):
+    """Distance::transformed_distance (src/Distance.h:6-11) compiled from the reference's header
+    against the oracle's restatement: bit-identical on fp32-representable and on arbitrary fp64
+    coordinates, at several magnitudes (no FMA contraction on either side)."""
+    R = _ref_or_skip(pto)
+    rng = np.random.default_rng(7)
+    for scale, as_f32 in ((1.0, True), (1000.0, True), (1.0, False), (1e6, False), (1e-6, False)):
+        A, B = _rand_points(pto, 20000, rng, scale), _rand_points(pto, 20000, rng, scale)
+        if as_f32:
+            A["ver"] = A["ver"].astype(np.float32); B["ver"] = B["ver"].astype(np.float32)
+        for i in range(len(A)):
+            a, b = A[i:i + 1], B[i:i + 1]
+            ref = R.ref_transformed_distance(a.ctypes.data, b.ctypes.data)
+            got = pto.transformed_distance(A[i], B[i])
+            assert ref == got and np.float64(ref).tobytes() == np.float64(got).tobytes()
+    # brute-force k-NN distances are this metric too
+    P, Q = _rand_points(pto, 500, rng, 10.0), _rand_points(pto, 20, rng, 10.0)
+    idx, d2 = pto.knn_bruteforce(P, Q, 5)
+    for qi in range(len(Q)):
+        for j in range(5):
+            assert d2[qi, j] == R.ref_transformed_distance(Q[qi:qi + 1].ctypes.data,
+                                                           P[idx[qi, j]:idx[qi, j] + 1].ctypes.data)
+
+
+def test_box_bound_and_helpers_match_reference_distance_h(pto):
+    """min_distance_to_rectangle (3-argument form, src/Distance.h:27-57), new_distance (:92-95),
+    transformed_distance(d) (:97): the oracle's restatements against the reference's code."""
+    R = _ref_or_skip(pto)
+    rng = np.random.default_rng(11)
+    for _ in range(5000):
+        p = _rand_points(pto, 1, rng, 3.0)
+        c = rng.standard_normal(3) * 3.0
+        h = np.abs(rng.standard_normal(3))
+        lo, hi = np.ascontiguousarray(c - h), np.ascontiguousarray(c + h)
+        d_ref, d_got = np.zeros(3), np.zeros(3)
+        ref = R.ref_min_distance_to_rectangle(p.ctypes.data, lo.ctypes.data, hi.ctypes.data,
+                                              d_ref.ctypes.data)
+        got, d_got = pto.min_distance_to_rectangle(p[0], lo, hi, d_got)
+        assert ref == got and np.array_equal(d_ref, d_got)
+        a, b, cc = rng.standard_normal(3)
+        assert R.ref_new_distance(abs(a), b, cc) == pto.lib().pto_new_distance(abs(a), b, cc)
+        assert R.ref_transformed_radius(a) == pto.lib().pto_transformed_radius(a)
+    assert R.ref_inverse_of_transformed_distance(9.0) == 3.0
