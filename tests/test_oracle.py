@@ -195,3 +195,22 @@ def test_box_bound_and_helpers_match_reference_distance_h(pto):
         assert R.ref_new_distance(abs(a), b, cc) == pto.lib().pto_new_distance(abs(a), b, cc)
         assert R.ref_transformed_radius(a) == pto.lib().pto_transformed_radius(a)
     assert R.ref_inverse_of_transformed_distance(9.0) == 3.0
+
+
+def test_golden_fixture_distances_are_the_reference_metric(pto, golden_dir):
+    """The committed fixtures' squared distances, recomputed pair by pair with the reference's
+    compiled Distance::transformed_distance, are bit-identical -- and ascending."""
+    R = _ref_or_skip(pto)
+    for path in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
+        z, P, Q = _load(path, pto)
+        for k in z["ks"]:
+            idx, d2 = z[f"idx_k{int(k)}"], z[f"d2_k{int(k)}"]
+            for qi in range(0, len(Q), 5):
+                for j in range(int(k)):
+                    if idx[qi, j] < 0:
+                        assert np.isinf(d2[qi, j])
+                        continue
+                    ref = R.ref_transformed_distance(Q[qi:qi + 1].ctypes.data,
+                                                     P[idx[qi, j]:idx[qi, j] + 1].ctypes.data)
+                    assert d2[qi, j] == ref, (os.path.basename(path), int(k), qi, j)
+                    assert j == 0 or d2[qi, j - 1] <= d2[qi, j]
