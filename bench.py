@@ -202,8 +202,15 @@ def run_cpu_leg(pkg, pto, P, Q, k, radius, steps, warmup):
         pto.blend(P, idx, d2)
         times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
+    # SURVEY 8 M4 also asks for the single-thread rate (the reference is single-threaded unless
+    # built with -DMULTI_THREADING=ON): the k-NN alone, one thread, on an eighth of the sample
+    Q1 = Q[: max(1, len(Q) // 8)]
+    t0 = time.perf_counter()
+    tree.knn(Q1, k, radius=r, exact_ties=False, nthreads=1, want_d2=False)
+    t1 = time.perf_counter() - t0
     tree.close()
     return {"value": len(Q) / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "single_thread_knn_value": len(Q1) / t1,
             "sample": f"{len(Q)} samples (unique-vertex queries, k={k}) against a {len(P)}-point "
                       f"window of the workload cloud; CGAL-style kd-tree (sliding midpoint, bucket "
                       f"10) + blend, OpenMP over samples; tree build {build_s:.2f} s excluded",
