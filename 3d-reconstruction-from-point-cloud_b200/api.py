@@ -44,7 +44,7 @@ SYNTH_HEIGHTFIELD, SYNTH_SKEWED = 0, 1
 # Every symbol include/points_transfer.h and include/pt_synth.h declare.
 ABI_SYMBOLS = (
     "pt_version", "pt_status_string", "pt_device_count", "pt_index_build", "pt_index_free",
-    "pt_index_get_info", "pt_knn", "pt_transfer", "pt_transfer_slab", "pt_index_build_device", "pt_query_device",
+    "pt_index_get_info", "pt_index_fallback_counts", "pt_knn", "pt_transfer", "pt_transfer_slab", "pt_index_build_device", "pt_query_device",
     "pt_merge_device", "pt_halo_route_device", "pt_halo_prepare_device",
     "pt_halo_merge_device", "pt_ghost_check_device", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
     "pt_synth_cloud_device", "pt_synth_samples_device", "pt_synth_pack_points_device",
@@ -104,6 +104,8 @@ def lib():
     L.pt_index_free.argtypes = [vp]
     L.pt_index_get_info.restype = i32
     L.pt_index_get_info.argtypes = [vp, ctypes.POINTER(IndexInfo)]
+    L.pt_index_fallback_counts.restype = i32
+    L.pt_index_fallback_counts.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32 * 2)]
     L.pt_knn.restype = i32
     L.pt_knn.argtypes = [vp, vp, sz, i32, dbl, vp, vp]
     L.pt_transfer.restype = i32
@@ -266,6 +268,13 @@ class Tree:
 
     def size(self):
         return int(self.info().n_points)
+
+    def fallback_counts(self):
+        """(samples re-run by the warp kernel, samples the grid kernel handed over) of the last
+        query launch on this index."""
+        out = (ctypes.c_uint32 * 2)()
+        _check(lib().pt_index_fallback_counts(self._h, ctypes.byref(out)), "pt_index_fallback_counts")
+        return int(out[0]), int(out[1])
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -12,9 +12,12 @@ namespace pt {
 
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_verbose{-1};
-static std::atomic<int> g_knn_variant{-1};  // -1 auto (default): scan or thread kernel; 5 scan, 2 thread, 0 warp
+static std::atomic<int> g_knn_variant{-1};  // -1 auto (default): grid kernel first; 6 grid, 5 scan, 2 thread, 0 warp
 static std::atomic<int> g_sort{1};    // 1 hand-written radix sort (default), 0 cub::DeviceRadixSort
-static std::atomic<int> g_order{2};   // 0 Morton, 1 Hilbert, 2 Hilbert + kd refinement (default)
+static std::atomic<int> g_order{1};   // 0 Morton, 1 Hilbert (default), 2 Hilbert + kd refinement (no cell tables)
+static std::atomic<int> g_grid{1};        // build the uniform-grid cell tables (pt_grid.cu)
+static std::atomic<int> g_grid_tma{1};    // stage candidate runs with cp.async.bulk (0: per-lane cp.async)
+static std::atomic<int> g_sort_bits{48};  // ordered key bits, from the top (cells contiguous down to level 16)
 
 bool verbose()
 {
@@ -42,6 +45,9 @@ int map_cuda_error(cudaError_t e)
 int opt_knn_variant() { return g_knn_variant.load(); }
 int opt_order() { return g_order.load(); }
 int opt_sort() { return g_sort.load(); }
+int opt_grid() { return g_grid.load(); }
+int opt_grid_tma() { return g_grid_tma.load(); }
+int opt_sort_bits() { return g_sort_bits.load(); }
 static std::atomic<int> g_host_chunks{8};   // host-buffer API: pipeline chunks per call (one stream each, up to 16)
 int opt_host_chunks() { return g_host_chunks.load(); }
 static std::atomic<int> g_queue_cap{1 << 20};   // tests: shrink the per-sample queue (exactness under spilling)
@@ -53,12 +59,15 @@ int set_option(const char *name, int value)
 {
     if (!name) return PT_ERR_INVALID_ARG;
     if (!strcmp(name, "knn_variant")) {
-        if (value != -1 && value != 0 && value != 2 && value != 5) return PT_ERR_INVALID_ARG;
+        if (value != -1 && value != 0 && value != 2 && value != 5 && value != 6) return PT_ERR_INVALID_ARG;
         g_knn_variant.store(value);
         return PT_OK;
     }
     if (!strcmp(name, "order")) { g_order.store(value); return PT_OK; }
     if (!strcmp(name, "sort")) { g_sort.store(value); return PT_OK; }
+    if (!strcmp(name, "grid")) { g_grid.store(value ? 1 : 0); return PT_OK; }
+    if (!strcmp(name, "grid_tma")) { g_grid_tma.store(value ? 1 : 0); return PT_OK; }
+    if (!strcmp(name, "sort_bits")) { g_sort_bits.store(value); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { g_queue_cap.store(value < 2 ? 2 : value); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { g_host_chunks.store(value < 1 ? 1 : (value > 64 ? 64 : value)); return PT_OK; }
@@ -71,6 +80,9 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "knn_variant")) { *value = g_knn_variant.load(); return PT_OK; }
     if (!strcmp(name, "order")) { *value = g_order.load(); return PT_OK; }
     if (!strcmp(name, "sort")) { *value = g_sort.load(); return PT_OK; }
+    if (!strcmp(name, "grid")) { *value = g_grid.load(); return PT_OK; }
+    if (!strcmp(name, "grid_tma")) { *value = g_grid_tma.load(); return PT_OK; }
+    if (!strcmp(name, "sort_bits")) { *value = g_sort_bits.load(); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { *value = g_smem_pad.load(); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { *value = g_queue_cap.load(); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { *value = g_host_chunks.load(); return PT_OK; }
@@ -90,6 +102,8 @@ static int grow(void **p, size_t *cap, size_t need)
     return PT_OK;
 }
 
+static void destroy_index(pt_index *ix);
+
 static int new_index(int device, pt_index **out)
 {
     int count = 0;
@@ -101,8 +115,19 @@ static int new_index(int device, pt_index **out)
     pt_index *ix = new (std::nothrow) pt_index();
     if (!ix) return PT_ERR_OUT_OF_MEMORY;
     ix->device = device;
-    PT_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    for (auto &ev : ix->ev) PT_CUDA(cudaEventCreate(&ev));
+    e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    for (auto &ev : ix->ev)
+        if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->fallback_word, 16);
+    if (e == cudaSuccess) e = cudaMemset(ix->fallback_word, 0, 16);
+    int sms = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {          // nothing leaks on a half-constructed handle
+        if (verbose()) fprintf(stderr, "[points_transfer] new_index: %s\n", cudaGetErrorString(e));
+        destroy_index(ix);
+        return map_cuda_error(e);
+    }
+    ix->sm_count = sms > 0 ? sms : 148;
     *out = ix;
     return PT_OK;
 }
@@ -112,22 +137,20 @@ static void destroy_index(pt_index *ix)
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    // sorted points and boxes come from the stream-ordered pool (pt_build.cu): back to it
+    for (auto &c : ix->cs) if (c) cudaStreamSynchronize(c);
+    // sorted points, boxes and cell tables come from the library's stream-ordered pool: back to it
     if (ix->pts) cudaFreeAsync(ix->pts, ix->stream);
     if (ix->boxes) cudaFreeAsync(ix->boxes, ix->stream);
+    if (ix->grid_mem) cudaFreeAsync(ix->grid_mem, ix->stream);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    {   // at most 2 GiB stay cached for the next build
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ix->device) == cudaSuccess)
-            cudaMemPoolTrimTo(pool, (size_t)2 << 30);
-        cudaGetLastError();
-    }
-    cudaFree(ix->attrs); cudaFree(ix->ids);
-    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_ovf);
+    pool_trim(ix->device, (size_t)2 << 30);   // at most 2 GiB stay cached for the next build
+    cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->fallback_word);
+    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out);
     for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
     for (auto &e : ix->cev) if (e) cudaEventDestroy(e);
     for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);
     if (ix->stream) cudaStreamDestroy(ix->stream);
+    cudaGetLastError();
     delete ix;
 }
 
@@ -148,6 +171,8 @@ static void fill_params(const pt_index *ix, QueryParams &qp)
     qp.w_levels = ix->w_levels;
     qp.t_levels = ix->t_levels;
     qp.pq_cap = opt_queue_cap();
+    qp.grid.n_tables = 0;      // launch_query plans the grid search
+    qp.grid.n_attempts = 0;
 }
 
 }  // namespace pt
@@ -265,10 +290,10 @@ int pt_index_get_info(const pt_index *ix, pt_index_info *info)
     info->coord_mode = ix->coord_f64 ? PT_COORD_F64 : PT_COORD_F32;
     info->device = ix->device;
     info->last_fallback_samples = -1;
-    if (ix->ws_ovf) {   // overflow counter of launch slot 0 (device word; this call may synchronise)
+    if (ix->fallback_word) {   // written by the last warp-kernel stage (device word; this call synchronises)
         uint32_t c = 0;
         if (cudaSetDevice(ix->device) == cudaSuccess &&
-            cudaMemcpy(&c, ix->ws_ovf, sizeof c, cudaMemcpyDeviceToHost) == cudaSuccess)
+            cudaMemcpy(&c, ix->fallback_word, sizeof c, cudaMemcpyDeviceToHost) == cudaSuccess)
             info->last_fallback_samples = (int)c;
         cudaGetLastError();
     }
@@ -281,10 +306,20 @@ int pt_index_get_info(const pt_index *ix, pt_index_info *info)
     return PT_OK;
 }
 
-static int query_device_slot(pt_index *ix, const double *queries_xyz, size_t m, int k, double radius,
-                             const double *radius2_per_query, int32_t *idx_out, double *d2_out,
-                             uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
-                             cudaStream_t stream, int slot)
+int pt_index_fallback_counts(const pt_index *ix, uint32_t out2[2])
+{
+    if (!ix || !out2) return PT_ERR_INVALID_ARG;
+    out2[0] = out2[1] = 0;
+    if (!ix->fallback_word) return PT_OK;
+    PT_CUDA(cudaSetDevice(ix->device));
+    PT_CUDA(cudaMemcpy(out2, ix->fallback_word, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return PT_OK;
+}
+
+static int query_device_on(pt_index *ix, const double *queries_xyz, size_t m, int k, double radius,
+                           const double *radius2_per_query, int32_t *idx_out, double *d2_out,
+                           uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
+                           cudaStream_t stream)
 {
     QueryParams qp{};
     fill_params(ix, qp);
@@ -295,7 +330,7 @@ static int query_device_slot(pt_index *ix, const double *queries_xyz, size_t m, 
     qp.r2 = radius_to_r2(radius);
     qp.idx_out = idx_out; qp.d2_out = d2_out; qp.rgba_out = rgba_out;
     qp.normal_out = normal_out; qp.cand_out = cand_out;
-    return launch_query(ix, qp, stream, slot);
+    return launch_query(ix, qp, stream);
 }
 
 int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, double radius,
@@ -306,9 +341,8 @@ int pt_query_device(pt_index *ix, const double *queries_xyz, size_t m, int k, do
     if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
     if ((rgba_out || normal_out) && !ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
     PT_CUDA(cudaSetDevice(ix->device));
-    PT_TRY(ensure_overflow_slots(ix, (uint32_t)m, 1));
-    return query_device_slot(ix, queries_xyz, m, k, radius, radius2_per_query, idx_out, d2_out,
-                             rgba_out, normal_out, cand_out, (cudaStream_t)stream, 0);
+    return query_device_on(ix, queries_xyz, m, k, radius, radius2_per_query, idx_out, d2_out,
+                           rgba_out, normal_out, cand_out, (cudaStream_t)stream);
 }
 
 int pt_merge_device(const pt_cand *lists, int n_lists, size_t m, int k, int32_t *idx_out,
@@ -412,48 +446,58 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
         if (!ix->cs[i]) PT_CUDA(cudaStreamCreateWithFlags(&ix->cs[i], cudaStreamNonBlocking));
         if (!ix->cev[i]) PT_CUDA(cudaEventCreateWithFlags(&ix->cev[i], cudaEventDisableTiming));
     }
-    PT_TRY(ensure_overflow_slots(ix, (uint32_t)chunk, n_streams));
-
-    PT_CUDA(cudaEventRecord(ix->ev[0], s));
-    for (int i = 0; i < n_streams; ++i) PT_CUDA(cudaStreamWaitEvent(ix->cs[i], ix->ev[0], 0));
-    for (int c = 0; c < n_chunks; ++c) {
-        const int si = c % NCS;
-        cudaStream_t st = ix->cs[si];
-        const size_t c0 = (size_t)c * chunk;
-        const size_t cm = m - c0 < chunk ? m - c0 : chunk;
-        double *qd = (double *)ix->ws_q + 3 * c0;
-        if (queries_are_xyz) {
-            PT_CUDA(cudaMemcpyAsync(qd, (const double *)queries + 3 * c0, cm * 24,
-                                    cudaMemcpyHostToDevice, st));
-        } else {
-            char *raw = (char *)ix->ws_raw + c0 * PT_POINT_STRIDE;
-            PT_CUDA(cudaMemcpyAsync(raw, (const char *)queries + c0 * PT_POINT_STRIDE,
-                                    cm * PT_POINT_STRIDE, cudaMemcpyHostToDevice, st));
-            PT_TRY(unpack_queries_aos(raw, cm, qd, st));
+    // Everything below may leave work in flight on the chunk streams: on any failure the
+    // streams are drained before the status is returned, so no copy is still writing into the
+    // caller's buffers after the call has reported an error (ABI: blocking on return).
+    auto issue = [&]() -> int {
+        PT_CUDA(cudaEventRecord(ix->ev[0], s));
+        for (int i = 0; i < n_streams; ++i) PT_CUDA(cudaStreamWaitEvent(ix->cs[i], ix->ev[0], 0));
+        for (int c = 0; c < n_chunks; ++c) {
+            const int si = c % NCS;
+            cudaStream_t st = ix->cs[si];
+            const size_t c0 = (size_t)c * chunk;
+            const size_t cm = m - c0 < chunk ? m - c0 : chunk;
+            double *qd = (double *)ix->ws_q + 3 * c0;
+            if (queries_are_xyz) {
+                PT_CUDA(cudaMemcpyAsync(qd, (const double *)queries + 3 * c0, cm * 24,
+                                        cudaMemcpyHostToDevice, st));
+            } else {
+                char *raw = (char *)ix->ws_raw + c0 * PT_POINT_STRIDE;
+                PT_CUDA(cudaMemcpyAsync(raw, (const char *)queries + c0 * PT_POINT_STRIDE,
+                                        cm * PT_POINT_STRIDE, cudaMemcpyHostToDevice, st));
+                PT_TRY(unpack_queries_aos(raw, cm, qd, st));
+            }
+            PT_TRY(query_device_on(ix, qd, cm, k, radius, nullptr,
+                                   idx_out ? (int32_t *)(o + off_idx) + c0 * k : nullptr,
+                                   need_d2 ? (double *)(o + off_d2) + c0 * k : nullptr,
+                                   rgba_out ? (uint8_t *)(o + off_rgba) + c0 * 4 : nullptr,
+                                   normal_out ? (float *)(o + off_nrm) + c0 * 3 : nullptr, nullptr, st));
+            if (ghost)
+                PT_TRY(launch_ghost_check(qd, (double *)(o + off_d2) + c0 * k, (uint32_t)cm, k,
+                                          radius_to_r2(radius), (const double *)(o + off_boxes),
+                                          ghost->n_ranks, ghost->self, ghost->halo,
+                                          (uint32_t *)(o + off_flag), st));
+            if (d2_out) PT_CUDA(cudaMemcpyAsync(d2_out + c0 * k, (double *)(o + off_d2) + c0 * k, cm * k * 8, cudaMemcpyDeviceToHost, st));
+            if (idx_out) PT_CUDA(cudaMemcpyAsync(idx_out + c0 * k, (int32_t *)(o + off_idx) + c0 * k, cm * k * 4, cudaMemcpyDeviceToHost, st));
+            if (normal_out) PT_CUDA(cudaMemcpyAsync(normal_out + c0 * 3, (float *)(o + off_nrm) + c0 * 3, cm * 12, cudaMemcpyDeviceToHost, st));
+            if (rgba_out) PT_CUDA(cudaMemcpyAsync(rgba_out + c0 * 4, (uint8_t *)(o + off_rgba) + c0 * 4, cm * 4, cudaMemcpyDeviceToHost, st));
         }
-        PT_TRY(query_device_slot(ix, qd, cm, k, radius, nullptr,
-                                 idx_out ? (int32_t *)(o + off_idx) + c0 * k : nullptr,
-                                 need_d2 ? (double *)(o + off_d2) + c0 * k : nullptr,
-                                 rgba_out ? (uint8_t *)(o + off_rgba) + c0 * 4 : nullptr,
-                                 normal_out ? (float *)(o + off_nrm) + c0 * 3 : nullptr, nullptr,
-                                 st, si));
-        if (ghost)
-            PT_TRY(launch_ghost_check(qd, (double *)(o + off_d2) + c0 * k, (uint32_t)cm, k,
-                                      radius_to_r2(radius), (const double *)(o + off_boxes),
-                                      ghost->n_ranks, ghost->self, ghost->halo,
-                                      (uint32_t *)(o + off_flag), st));
-        if (d2_out) PT_CUDA(cudaMemcpyAsync(d2_out + c0 * k, (double *)(o + off_d2) + c0 * k, cm * k * 8, cudaMemcpyDeviceToHost, st));
-        if (idx_out) PT_CUDA(cudaMemcpyAsync(idx_out + c0 * k, (int32_t *)(o + off_idx) + c0 * k, cm * k * 4, cudaMemcpyDeviceToHost, st));
-        if (normal_out) PT_CUDA(cudaMemcpyAsync(normal_out + c0 * 3, (float *)(o + off_nrm) + c0 * 3, cm * 12, cudaMemcpyDeviceToHost, st));
-        if (rgba_out) PT_CUDA(cudaMemcpyAsync(rgba_out + c0 * 4, (uint8_t *)(o + off_rgba) + c0 * 4, cm * 4, cudaMemcpyDeviceToHost, st));
-    }
-    for (int i = 0; i < n_streams; ++i) {
-        PT_CUDA(cudaEventRecord(ix->cev[i], ix->cs[i]));
-        PT_CUDA(cudaStreamWaitEvent(s, ix->cev[i], 0));
-    }
+        for (int i = 0; i < n_streams; ++i) {
+            PT_CUDA(cudaEventRecord(ix->cev[i], ix->cs[i]));
+            PT_CUDA(cudaStreamWaitEvent(s, ix->cev[i], 0));
+        }
+        return PT_OK;
+    };
     uint32_t flag = 0;
-    if (ghost) PT_CUDA(cudaMemcpyAsync(&flag, o + off_flag, sizeof flag, cudaMemcpyDeviceToHost, s));
-    PT_CUDA(cudaEventRecord(ix->ev[3], s));
+    int rc = issue();
+    if (rc == PT_OK && ghost) rc = map_cuda_error(cudaMemcpyAsync(&flag, o + off_flag, sizeof flag, cudaMemcpyDeviceToHost, s));
+    if (rc == PT_OK) rc = map_cuda_error(cudaEventRecord(ix->ev[3], s));
+    if (rc != PT_OK) {
+        for (int i = 0; i < n_streams; ++i) cudaStreamSynchronize(ix->cs[i]);
+        cudaStreamSynchronize(s);
+        cudaGetLastError();
+        return rc;
+    }
     PT_CUDA(cudaStreamSynchronize(s));
     if (ghost && ghost->needs_exchange) *ghost->needs_exchange = flag ? 1 : 0;
     ix->last_h2d_ms = 0.f;          // overlapped with the kernels: only the total is meaningful

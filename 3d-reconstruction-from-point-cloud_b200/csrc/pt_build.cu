@@ -13,6 +13,7 @@
 #include <cfloat>
 #include <chrono>
 #include <cmath>
+#include <mutex>
 
 #include "pt_index.cuh"
 
@@ -417,13 +418,15 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const Box *child, uint32_t
 }
 
 // ---- K2: sort ------------------------------------------------------------------------------
+// Only key bits [first_bit, 63) are ordered: the grid tables need cells contiguous down to level
+// 16 (48 key bits) and the 32-point leaves gain nothing from the order inside a cell that small.
 static int sort_pairs(unsigned long long *&keys, unsigned long long *keys_alt, uint32_t *&vals,
-                      uint32_t *vals_alt, uint32_t n, void *ws, cudaStream_t s)
+                      uint32_t *vals_alt, uint32_t n, int first_bit, void *ws, cudaStream_t s)
 {
     if (opt_sort() != 0) {   // hand-written LSD radix sort (pt_sort.cu), the default
         unsigned long long *ko = nullptr;
         uint32_t *vo = nullptr;
-        int rc = radix_sort_pairs(keys, keys_alt, vals, vals_alt, n, 63, ws, s, &ko, &vo);
+        int rc = radix_sort_pairs(keys, keys_alt, vals, vals_alt, n, first_bit, 63, ws, s, &ko, &vo);
         if (rc != PT_OK) return rc;
         keys = ko;
         vals = vo;
@@ -433,10 +436,10 @@ static int sort_pairs(unsigned long long *&keys, unsigned long long *keys_alt, u
     cub::DoubleBuffer<unsigned long long> dk(keys, keys_alt);
     cub::DoubleBuffer<uint32_t> dv(vals, vals_alt);
     size_t tmp_bytes = 0;
-    PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, 63, s));
+    PT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, first_bit, 63, s));
     void *tmp = nullptr;
     PT_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)n, 0, 63, s);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)n, first_bit, 63, s);
     count_launch(9);
     cudaError_t e2 = cudaStreamSynchronize(s);
     cudaFree(tmp);
@@ -449,26 +452,52 @@ static int sort_pairs(unsigned long long *&keys, unsigned long long *keys_alt, u
 
 static inline unsigned int cdiv(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
 
-// Build temporaries (sort keys / values / counters: ~24 bytes per point) come from the device's
-// stream-ordered memory pool with an unlimited release threshold, so a rebuild reuses them
-// instead of paying cudaMalloc / cudaFree (3-30 ms per GB, host-synchronous) every time.
-static int temp_alloc(void **p, size_t bytes, cudaStream_t s)
+// Build temporaries (sort keys / values / counters: ~24 bytes per point), the sorted points, the
+// boxes, the cell tables and the per-launch hand-over lists come from a PRIVATE stream-ordered
+// memory pool per device with an unlimited release threshold, so a rebuild reuses them instead
+// of paying cudaMalloc / cudaFree (3-30 ms per GB, host-synchronous) every time -- and the host
+// application's default pool keeps its own retention policy.
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64] = {};
+
+static int device_pool(int dev, cudaMemPool_t *out)
 {
-    static bool pool_set[64] = {};
-    int dev = 0;
-    PT_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !pool_set[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-        pool_set[dev] = true;
+    if (dev < 0 || dev >= 64) return PT_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        PT_CUDA(cudaMemPoolCreate(&pool, &props));
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        g_pools[dev] = pool;
     }
-    PT_CUDA(cudaMallocAsync(p, bytes, s));
+    *out = g_pools[dev];
     return PT_OK;
 }
+
+int pool_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    int dev = 0;
+    PT_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    PT_TRY(device_pool(dev, &pool));
+    PT_CUDA(cudaMallocFromPoolAsync(p, bytes ? bytes : 16, pool, s));
+    return PT_OK;
+}
+
+void pool_trim(int device, size_t keep_bytes)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (device >= 0 && device < 64 && g_pools[device]) cudaMemPoolTrimTo(g_pools[device], keep_bytes);
+    cudaGetLastError();
+}
+
+static int temp_alloc(void **p, size_t bytes, cudaStream_t s) { return pool_alloc(p, bytes, s); }
 
 template <typename In, typename Out>
 static int build_impl(pt_index *ix, In in, uint32_t n)
@@ -488,6 +517,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     ix->n_leaves = cdiv(n, LEAF);
     ix->coord_f64 = sizeof(Out) == 32;
     for (int a = 0; a < 3; ++a) { ix->bb_lo[a] = 0; ix->bb_hi[a] = 0; }
+    ix->grid = GridParams{};
     ix->pyr = Pyramid{};
     ix->w_levels = 0;
     ix->t_levels = 0;
@@ -501,7 +531,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     PT_CUDA(cudaMemcpyAsync(acc, &h_acc, sizeof h_acc, cudaMemcpyHostToDevice, s));
     {
         unsigned int blocks = cdiv(n, 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks > (unsigned)ix->sm_count * 8u) blocks = (unsigned)ix->sm_count * 8u;
         bbox_kernel<In><<<blocks, 256, 0, s>>>(in, n, acc);
         count_launch();
     }
@@ -539,12 +569,17 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     morton_kernel<In><<<cdiv(n, 256), 256, 0, s>>>(in, n, kp, keys, vals);
     count_launch();
     lap("keys");
-    int rc = sort_pairs(keys, keys_alt, vals, vals_alt, n, sort_ws, s);
+    struct ArenaGuard {    // the sort arena goes back to the pool on every exit path
+        char *p; cudaStream_t s;
+        ~ArenaGuard() { if (p) cudaFreeAsync(p, s); }
+    } arena_guard{arena, s};
+    int sort_bits = opt_sort_bits();
+    sort_bits = sort_bits < 8 ? 8 : (sort_bits > 63 ? 63 : sort_bits);
+    const int passes = (sort_bits + 7) / 8;                      // 8-bit digits from the top of the key down
+    const int first_bit = (kp.order == 2 || passes >= 8) ? 0 : 63 - 8 * passes;
+    int rc = sort_pairs(keys, keys_alt, vals, vals_alt, n, first_bit, sort_ws, s);
     lap("sort");
-    if (rc != PT_OK) {
-        cudaFreeAsync(arena, s);
-        return rc;
-    }
+    if (rc != PT_OK) return rc;
 
     // gather into leaves
     size_t n_pad = (size_t)ix->n_leaves * LEAF;
@@ -556,6 +591,9 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     lap("gather");
     if (kp.order == 2) PT_TRY(kd_refine<Out>(pts, (uint32_t)n_pad, s));
     lap("kd refine");
+    // cell tables over the curve order (the kd refinement reorders inside blocks: no cell runs)
+    if (kp.order != 2) PT_TRY(build_grid(ix, keys, first_bit, kp.lo, kp.inv_cell, ext));
+    lap("grid tables");
 
     // box pyramid
     uint64_t total = 0;
@@ -596,16 +634,10 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     lap("boxes");
     PT_CUDA(cudaEventElapsedTime(&ix->build_ms, ix->ev[0], ix->ev[1]));
     cudaFreeAsync(arena, s);
-    {   // keep at most 2 GiB of temporaries cached for the next build; the rest goes back
-        cudaMemPool_t pool;
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            cudaStreamSynchronize(s);
-            cudaMemPoolTrimTo(pool, (size_t)2 << 30);
-        }
-        cudaGetLastError();
-    }
-    ix->device_bytes = sizeof(Out) * n_pad + sizeof(Box) * total +
+    arena_guard.p = nullptr;
+    cudaStreamSynchronize(s);
+    pool_trim(ix->device, (size_t)2 << 30);   // at most 2 GiB of temporaries stay cached for the next build
+    ix->device_bytes = sizeof(Out) * n_pad + sizeof(Box) * total + ix->grid_bytes +
                        (ix->attrs ? sizeof(pt_attr) * (size_t)n : 0) +
                        (ix->ids ? sizeof(int32_t) * (size_t)n : 0);
     return PT_OK;

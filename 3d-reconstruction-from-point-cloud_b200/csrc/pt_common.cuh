@@ -64,6 +64,42 @@ struct Pyramid {
     int        n_levels;
 };
 
+// ---- uniform grid over the curve-sorted cloud (pt_grid.cu) ----------------------------------
+// A cell of level l is the set of points whose 21-bit lattice coordinates share their top l bits
+// per axis: one contiguous run of the sorted cloud (Morton and Hilbert keys are both
+// hierarchical).  A table holds one 32-byte bucket per occupied PARENT cell (level l - 1), found
+// by hashing the parent's lattice coordinates; the bucket locates the runs of its 8 children.
+struct __align__(16) GridBucket {
+    unsigned long long key;    // parent coordinates x | y << 21 | z << 42; ~0 = empty slot
+    uint32_t           start;  // first point of the parent's run
+    uint32_t           perm;   // bits 3o..3o+2: curve rank of child octant o (x&1 | y&1 << 1 | z&1 << 2);
+                               // bits 24+o: octant o holds points
+    uint16_t           cum[8]; // cum[0] = points of the parent (0xffff: too many, bucket unusable);
+                               // cum[r], r >= 1 = points in the children of rank < r
+};
+static_assert(sizeof(GridBucket) == 32, "one sector per bucket");
+
+constexpr int GRID_MAX_TABLES = 4;
+constexpr int GRID_MAX_ATTEMPTS = 4;
+struct GridTable {
+    const GridBucket *buckets;
+    uint32_t          cap;     // slots (linear probing, load <= 1/2)
+    int               level;   // level of the CHILD cells the table resolves
+};
+struct GridParams {
+    GridTable tab[GRID_MAX_TABLES];   // finest first
+    int       n_tables;
+    double    lo[3];           // lattice origin (bbox minimum)
+    double    inv_cell21;      // 2^21 / extent
+    double    cell21;          // extent / 2^21
+    double    slack;           // absolute safety margin of the cell-boundary distances
+    // search schedule of one launch: attempt a looks at the (2 rc + 1)^3 block of level
+    // tab[att_tab[a]].level around the sample; the next attempt runs only if the k-th candidate
+    // is not provably final
+    int       n_attempts;
+    unsigned char att_tab[GRID_MAX_ATTEMPTS], att_rc[GRID_MAX_ATTEMPTS];
+};
+
 struct QueryParams {
     const void    *pts;        // PointF* or PointD*, n_pad records
     const pt_attr *attrs;      // original (local) order, may be null
@@ -74,6 +110,9 @@ struct QueryParams {
     int            w_levels;   // number of 32-wide levels used by the warp traversal
     int            t_levels;   // number of 8-wide levels used by the thread traversal
     int            pq_cap;     // queue entries a sample may hold (<= the compiled capacity)
+    GridParams     grid;       // n_tables == 0: no grid
+    const uint32_t *qlist;     // optional: the launch answers samples qlist[0 .. *qcount) only
+    const uint32_t *qcount;
     const double  *queries;    // m * 3
     const double  *r2_per_query;
     uint32_t       m;

@@ -16,17 +16,21 @@ struct pt_index {
     pt::Box     *boxes = nullptr;    // all pyramid levels, level 0 first
     pt::Pyramid  pyr{};
     double       bb_lo[3]{}, bb_hi[3]{};
+    pt::GridBucket *grid_mem = nullptr;   // all cell tables (pt_grid.cu), pooled allocation
+    size_t       grid_bytes = 0;
+    pt::GridParams grid{};                // tables of this index (n_tables == 0: none)
+    uint64_t     level_cells[22]{};       // occupied cells per lattice level (0: not counted)
+    uint32_t    *fallback_word = nullptr; // device: samples the last launch handed to the warp kernel
     uint64_t     device_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t  ev[4]{};
     float        build_ms = 0, last_query_ms = 0, last_h2d_ms = 0, last_d2h_ms = 0;
 
+    int          sm_count = 148;
     // grow-only workspaces for the host-buffer API
     void  *ws_raw = nullptr;   size_t ws_raw_bytes = 0;    // uploaded 80-byte query records
     void  *ws_q = nullptr;     size_t ws_q_bytes = 0;      // m*3 doubles
     void  *ws_out = nullptr;   size_t ws_out_bytes = 0;    // idx | d2 | rgba | normal
-    void  *ws_ovf = nullptr;   size_t ws_ovf_bytes = 0;    // queue-overflow count + sample list,
-    uint32_t ovf_slot_words = 0;                           //   one slot per concurrent launch
     cudaStream_t cs[16]{};                                  // chunk streams of the host-buffer API
     cudaEvent_t  cev[16]{};
 };
@@ -71,8 +75,14 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
                       bool *representable);
 int unpack_queries_aos(const void *raw80_dev, size_t m, double *xyz_dev, cudaStream_t s);
 
-int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots);
-int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot = 0);
+int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s);
+// Stream-ordered allocation from the library's PRIVATE memory pool of the current device (the
+// application's default pool is never touched); release with cudaFreeAsync.
+int pool_alloc(void **p, size_t bytes, cudaStream_t s);
+void pool_trim(int device, size_t keep_bytes);
+int build_grid(pt_index *ix, const unsigned long long *keys, int low_shift, const double lo[3],
+               double inv_cell21, double extent);
+int grid_plan(const pt_index *ix, int k, double r2, GridParams &gp);
 int launch_merge(const pt_cand *lists, int n_lists, uint32_t m, int k, int32_t *idx_out,
                  double *d2_out, uint8_t *rgba_out, float *normal_out, pt_cand *cand_out,
                  cudaStream_t s);
@@ -91,8 +101,8 @@ int launch_halo_merge(pt_cand *own, const pt_cand *back, const int32_t *sel, con
 
 size_t radix_sort_workspace_bytes(uint32_t n);
 int radix_sort_pairs(unsigned long long *keys, unsigned long long *keys_alt, uint32_t *vals,
-                     uint32_t *vals_alt, uint32_t n, int bits, void *workspace, cudaStream_t s,
-                     unsigned long long **keys_out, uint32_t **vals_out);
+                     uint32_t *vals_alt, uint32_t n, int first_bit, int end_bit, void *workspace,
+                     cudaStream_t s, unsigned long long **keys_out, uint32_t **vals_out);
 
 int  get_option(const char *name, int *value);
 int  set_option(const char *name, int value);
@@ -101,6 +111,9 @@ int  opt_order();
 int  opt_sort();
 int  opt_smem_pad();
 int  opt_queue_cap();
+int  opt_grid();
+int  opt_grid_tma();
+int  opt_sort_bits();
 int  debug_stats(unsigned long long *out16, int reset);
 
 }  // namespace pt

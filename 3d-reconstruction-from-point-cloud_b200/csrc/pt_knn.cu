@@ -2,7 +2,10 @@
 // `K_neighbor_search search(tree, q, K)` loop, /root/reference src/pointsTransfer.cpp:470-479,
 // metric src/Distance.h:6-11, pruning bound src/Distance.h:27-57).
 //
-// Three kernels share the helpers in this file:
+// Four kernels share the helpers in this file:
+//   variant 6 ("grid",   pt_knn_grid.cuh)  : one warp per sample over the uniform-grid cell
+//     tables, candidate runs staged in shared memory by bulk async copies; the default first
+//     stage -- samples it cannot prove final go to the kernels below;
 //   variant 5 ("scan",   pt_knn_scan.cuh)  : one thread per sample, unsorted top-k slots;
 //   variant 2 ("thread", pt_knn_thread.cuh): one thread per sample, top-k heap;
 //     both walk the box pyramid with pt_knn_traverse.cuh, state in shared-memory columns;
@@ -328,12 +331,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) knn_warp_kernel(const Qu
 // Re-runs the samples listed by the thread kernel (queue overflow), grid-stride over the list.
 template <typename PT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-knn_warp_list_kernel(const QueryParams P, const uint32_t *count, const uint32_t *list)
+knn_warp_list_kernel(const QueryParams P, const uint32_t *count, const uint32_t *list,
+                     uint32_t *stat_out, const uint32_t *count_stage1)
 {
     __shared__ float s_lb[WARPS_PER_BLOCK][MAX_W_LEVELS][32];
     const unsigned lane = threadIdx.x & 31;
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t n = min(*count, P.m);
+    if (stat_out && blockIdx.x == 0 && threadIdx.x == 0) {   // pt_index_info / pt_index_fallback_counts
+        stat_out[0] = n;
+        stat_out[1] = count_stage1 ? *count_stage1 : 0u;
+    }
     for (uint32_t w = blockIdx.x * WARPS_PER_BLOCK + wib; w < n; w += gridDim.x * WARPS_PER_BLOCK)
         warp_query<PT>(P, list[w], lane, s_lb[wib]);
 }
@@ -355,53 +363,54 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 #include "pt_knn_traverse.cuh"
 #include "pt_knn_thread.cuh"
 #include "pt_knn_scan.cuh"
+#include "pt_knn_grid.cuh"
 namespace pt {
 
-// Scan (variant 5) / thread (variant 2) kernel, then the warp kernel over the samples that could
-// not discharge their queue proof obligation.  The overflow list lives in the index (grown on demand).
+// Launch plan.  Every launch gets its OWN hand-over workspace (two sample lists with their
+// counters) from the library's stream-ordered pool, so launches of one index that are in flight
+// on different streams never share state:
+//   grid kernel          --(samples it cannot prove final: list 1)-->
+//   scan / thread kernel --(samples whose queue proof obligation failed: list 2)-->
+//   warp kernel over list 2.
 template <typename PT>
-static int launch_with_fallback(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s,
-                                int slot)
+static int launch_chain(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s)
 {
-    if ((size_t)(slot + 1) * ix->ovf_slot_words * sizeof(uint32_t) > ix->ws_ovf_bytes ||
-        qp.m + 4 > ix->ovf_slot_words)
-        return PT_ERR_INVALID_ARG;   // ensure_overflow_slots() was not called for this launch
-    uint32_t *count = (uint32_t *)ix->ws_ovf + (size_t)slot * ix->ovf_slot_words;
-    uint32_t *list = count + 4;
-    PT_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));
-    if (variant == 5) {
-        PT_TRY(launch_scan<PT>(qp, count, list, s));
-    } else {
-        PT_TRY(launch_thread<PT>(qp, count, list, s));
+    const size_t words = (size_t)qp.m + 4;
+    uint32_t *ws = nullptr;
+    PT_TRY(pool_alloc((void **)&ws, sizeof(uint32_t) * 2 * words, s));
+    uint32_t *count1 = ws, *list1 = ws + 4, *count2 = ws + words, *list2 = count2 + 4;
+    int rc = PT_OK;
+    cudaError_t e = cudaMemsetAsync(count1, 0, 4 * sizeof(uint32_t), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(count2, 0, 4 * sizeof(uint32_t), s);
+    if (e != cudaSuccess) rc = map_cuda_error(e);
+    QueryParams q2 = qp;
+    const bool grid_first = variant == 6;
+    if (rc == PT_OK && variant == 6) {
+        rc = launch_grid<PT>(qp, ix->sm_count, count1, list1, s);
+        q2.qlist = list1;
+        q2.qcount = count1;
+        const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
+        variant = (qp.k > 16 || !bounded) ? 5 : 2;
     }
-    knn_warp_list_kernel<PT><<<148 * 4, WARPS_PER_BLOCK * 32, 0, s>>>(qp, count, list);
-    count_launch();
-    PT_CUDA(cudaGetLastError());
-    return PT_OK;
+    if (rc == PT_OK) rc = variant == 5 ? launch_scan<PT>(q2, count2, list2, s) : launch_thread<PT>(q2, count2, list2, s);
+    if (rc == PT_OK) {
+        knn_warp_list_kernel<PT><<<ix->sm_count * 4, WARPS_PER_BLOCK * 32, 0, s>>>(qp, count2, list2, ix->fallback_word,
+                                                                                         grid_first ? count1 : nullptr);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) rc = map_cuda_error(e);
+    }
+    cudaFreeAsync(ws, s);
+    return rc;
 }
 
-// Sizes the overflow workspace for `slots` concurrent launches of up to m_per_slot samples.
-// Reallocates (device-synchronising) only when it has to grow.
-int ensure_overflow_slots(pt_index *ix, uint32_t m_per_slot, int slots)
+int launch_query(pt_index *ix, const QueryParams &qp_in, cudaStream_t s)
 {
-    uint32_t words = m_per_slot + 4;
-    if (words < ix->ovf_slot_words) words = ix->ovf_slot_words;
-    size_t need = sizeof(uint32_t) * (size_t)words * slots;
-    if (need > ix->ws_ovf_bytes) {
-        if (ix->ws_ovf) cudaFree(ix->ws_ovf);
-        ix->ws_ovf = nullptr;
-        ix->ws_ovf_bytes = 0;
-        PT_CUDA(cudaMalloc(&ix->ws_ovf, need));
-        ix->ws_ovf_bytes = need;
-    }
-    ix->ovf_slot_words = words;
-    return PT_OK;
-}
-
-int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
-{
-    if (qp.m == 0) return PT_OK;
-    if (qp.k < 1 || qp.k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
+    if (qp_in.m == 0) return PT_OK;
+    if (qp_in.k < 1 || qp_in.k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
+    QueryParams qp = qp_in;
+    qp.qlist = nullptr;
+    qp.qcount = nullptr;
     if (ix->n == 0) {
         size_t total = (size_t)qp.m * qp.k;
         empty_result_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(qp);
@@ -410,18 +419,21 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
         return PT_OK;
     }
     int variant = opt_knn_variant();
+    const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
+    const bool have_grid = (variant < 0 || variant == 6) && grid_plan(ix, qp.k, qp.r2, qp.grid) > 0;
+    if (!have_grid) qp.grid.n_attempts = 0;
+    if (variant == 6 && !have_grid) variant = -1;
     if (variant < 0) {
-        // auto (measured):
+        // auto (measured): the grid kernel first whenever the index has
+        // cell tables.  Without them (tiny clouds, kd-refined order):
         //  * up to ~12 k samples a launch is one partial wave and pays a thread-kernel block's
-        //    full latency (0.23 ms at cfg2's cloud); the warp kernel -- 32 lanes per sample --
-        //    answers it in 0.14-0.19 ms (cfg1: 0.079 vs 0.136 ms);
+        //    full latency; the warp kernel -- 32 lanes per sample -- answers it sooner;
         //  * the scan kernel is 3-9 % ahead of the thread kernel on launches that fill the GPU
         //    and 23 % at k = 32;
-        //  * on mid-size launches (the ~25 k sample chunks of the host pipeline), on
-        //    radius-bounded searches, which mostly end with short lists, and on slab indexes
-        //    with an id map the thread kernel's exact entries win at k <= 16.
-        const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
-        if (qp.m <= 12288u) variant = 0;
+        //  * on mid-size launches, on radius-bounded searches, which mostly end with short
+        //    lists, and on slab indexes with an id map the thread kernel wins at k <= 16.
+        if (have_grid) variant = 6;
+        else if (qp.m <= 12288u) variant = 0;
         else variant = (qp.k > 16 || (!bounded && qp.m >= 100000u && qp.ids == nullptr)) ? 5 : 2;
     }
     if (variant == 0) {
@@ -434,8 +446,7 @@ int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s, int slot)
         PT_CUDA(cudaGetLastError());
         return PT_OK;
     }
-    return ix->coord_f64 ? launch_with_fallback<PointD>(ix, qp, variant, s, slot)
-                         : launch_with_fallback<PointF>(ix, qp, variant, s, slot);
+    return ix->coord_f64 ? launch_chain<PointD>(ix, qp, variant, s) : launch_chain<PointF>(ix, qp, variant, s);
 }
 
 // ---- K5: merge per-slab candidate lists (multi-GPU exchange epilogue) -------------------------

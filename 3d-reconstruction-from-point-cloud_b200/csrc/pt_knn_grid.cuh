@@ -1,0 +1,522 @@
+// pt_knn_grid.cuh -- variant 6 ("grid"): one warp per sample over the uniform-grid cell tables
+// (pt_grid.cu).  Replaces, for samples whose neighbourhood has ordinary density, the kd-tree
+// descent of `K_neighbor_search search(tree, q, K)` (/root/reference src/pointsTransfer.cpp:474);
+// the termination test is Distance::min_distance_to_rectangle (src/Distance.h:27-57) evaluated
+// on the block of cells that was searched.
+//
+//   1. cell of the sample in O(1) from its lattice coordinates; lane c looks up cell c of the
+//      (2 rc + 1)^3 block around it: one 32-byte bucket per parent cell (<= 8 sectors for 3^3)
+//      gives (start, count) of the cell's run in the curve-sorted cloud;
+//   2. a warp scan of the counts places the runs back to back in the warp's shared-memory
+//      staging area and every lane that owns a run issues ONE bulk copy for it
+//      (cp.async.bulk global -> shared, completion on an mbarrier; a run is contiguous and
+//      16-byte aligned because records are float4 / 2 x double2);
+//   3. lanes take the staged candidates round-robin: exact fp64 metric (src/Distance.h:6-11),
+//      then a 32-bit selection key = fp32 bits of d2 rounded DOWN, low 8 bits replaced by the
+//      candidate's slot.  Each lane sorts its <= 8 keys with a min/max network; the k + 1
+//      smallest keys of the warp are extracted by k + 1 rounds of REDUX.MIN, the owner lane
+//      popping its head.  Truncation is monotone, so distinct truncated keys order the exact
+//      distances; if two neighbouring winners (or winner k and k + 1) share a truncated key the
+//      sample is redone by an exact (d2, index) extraction;
+//   4. final iff the k-th d2 (or the radius bound while the list is short) is <= the squared
+//      distance from the sample to the boundary of the searched block (shrunk by a safety
+//      margin); otherwise the next attempt of the launch's schedule searches a larger block,
+//      and a sample that exhausts the schedule, meets a dense bucket or more than GRID_CAP
+//      candidates is handed to the box-pyramid kernels (exact for any geometry);
+//   5. winners' attributes gathered one per lane; the frozen blend's sequential fp64 sums run
+//      one component per lane over a transposed shared-memory tile (bit-identical to BlendAcc).
+#pragma once
+
+namespace pt {
+
+constexpr int GRID_CAP = 256;         // staged candidates per sample (8-bit slot numbers)
+#ifndef PT_GRID_WARPS
+#define PT_GRID_WARPS 4
+#endif
+constexpr int GRID_WARPS = PT_GRID_WARPS;
+constexpr uint32_t GKEY_NONE = 0xffffffffu;
+
+// ---- async-copy plumbing ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void ldgsts16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldgsts_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// ---- staged records ---------------------------------------------------------------------------
+template <typename PT> struct GridRec;
+template <> struct GridRec<PointF> {
+    static __device__ __forceinline__ void load(const PointF *c, uint32_t j, double &x, double &y,
+                                                double &z, int &idx)
+    {
+        const float4 v = *reinterpret_cast<const float4 *>(c + j);
+        x = (double)v.x; y = (double)v.y; z = (double)v.z;
+        idx = __float_as_int(v.w);
+    }
+};
+template <> struct GridRec<PointD> {
+    static __device__ __forceinline__ void load(const PointD *c, uint32_t j, double &x, double &y,
+                                                double &z, int &idx)
+    {
+        const double2 *p = reinterpret_cast<const double2 *>(c + j);
+        const double2 a = p[0], b = p[1];
+        x = a.x; y = a.y; z = b.x;
+        idx = __double2loint(b.y);
+    }
+};
+
+__device__ __forceinline__ uint32_t grid_hash_q(unsigned long long k)   // = grid_hash of pt_grid.cu
+{
+    uint32_t h = (uint32_t)k * 0x9E3779B1u ^ (uint32_t)(k >> 32) * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du;
+    h ^= h >> 12; h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return h;
+}
+
+// (start, count) of the run of cell (cx, cy, cz) at the table's level; count 0 when the cell is
+// empty, 0xffffffff when its bucket is unusable (too many points for the 16-bit counts).
+__device__ __forceinline__ void grid_lookup(const GridBucket *buckets, uint32_t cap, uint32_t cx,
+                                            uint32_t cy, uint32_t cz, uint32_t &start, uint32_t &cnt)
+{
+    const unsigned long long pkey = (unsigned long long)(cx >> 1) | ((unsigned long long)(cy >> 1) << 21) |
+                                    ((unsigned long long)(cz >> 1) << 42);
+    const unsigned oct = (cx & 1u) | ((cy & 1u) << 1) | ((cz & 1u) << 2);
+    uint32_t b = __umulhi(grid_hash_q(pkey), cap);
+    start = 0;
+    cnt = 0;
+    for (;;) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(buckets + b);
+        const uint4 a = __ldg(p), c = __ldg(p + 1);
+        const unsigned long long key = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
+        if (key == pkey) {
+            if (((a.w >> (24 + oct)) & 1u) == 0u) return;
+            const unsigned rank = (a.w >> (3 * oct)) & 7u;
+            const uint32_t total = c.x & 0xffffu;
+            if (total == 0xffffu) { cnt = 0xffffffffu; return; }
+            const unsigned long long lo = (unsigned long long)c.x | ((unsigned long long)c.y << 32);
+            const unsigned long long hi = (unsigned long long)c.z | ((unsigned long long)c.w << 32);
+            const unsigned r1 = rank + 1;
+            const uint32_t beg = rank ? (uint32_t)((rank < 4 ? lo >> (16 * rank) : hi >> (16 * (rank - 4))) & 0xffffu) : 0u;
+            const uint32_t end = rank < 7 ? (uint32_t)((r1 < 4 ? lo >> (16 * r1) : hi >> (16 * (r1 - 4))) & 0xffffu) : total;
+            start = a.z + beg;
+            cnt = end - beg;
+            return;
+        }
+        if (key == ~0ull) return;
+        if (++b == cap) b = 0;
+    }
+}
+
+template <int C> __device__ __forceinline__ void gkey_sort(uint32_t (&h)[C]);
+#define PT_GCAS(i, j) { const uint32_t lo_ = min(h[i], h[j]), hi_ = max(h[i], h[j]); h[i] = lo_; h[j] = hi_; }
+template <> __device__ __forceinline__ void gkey_sort<1>(uint32_t (&)[1]) {}
+template <> __device__ __forceinline__ void gkey_sort<2>(uint32_t (&h)[2]) { PT_GCAS(0, 1) }
+template <> __device__ __forceinline__ void gkey_sort<4>(uint32_t (&h)[4])
+{
+    PT_GCAS(0, 1) PT_GCAS(2, 3) PT_GCAS(0, 2) PT_GCAS(1, 3) PT_GCAS(1, 2)
+}
+template <> __device__ __forceinline__ void gkey_sort<8>(uint32_t (&h)[8])   // Batcher, 19 exchanges
+{
+    PT_GCAS(0, 1) PT_GCAS(2, 3) PT_GCAS(4, 5) PT_GCAS(6, 7)
+    PT_GCAS(0, 2) PT_GCAS(1, 3) PT_GCAS(4, 6) PT_GCAS(5, 7)
+    PT_GCAS(1, 2) PT_GCAS(5, 6)
+    PT_GCAS(0, 4) PT_GCAS(1, 5) PT_GCAS(2, 6) PT_GCAS(3, 7)
+    PT_GCAS(2, 4) PT_GCAS(3, 5)
+    PT_GCAS(1, 2) PT_GCAS(3, 4) PT_GCAS(5, 6)
+}
+#undef PT_GCAS
+
+// Fast selection on truncated keys.  On return lane r < k holds the key of the r-th smallest
+// candidate (GKEY_NONE past the end) and `amb` tells whether some neighbouring pair of the first
+// k + 1 keys shares its truncated distance (then the order / the cut is not proven).
+template <typename PT, int C>
+__device__ __forceinline__ void grid_select(const PT *cand, uint32_t total, double qx, double qy,
+                                            double qz, double r2, int k, unsigned lane,
+                                            uint32_t &mine, bool &amb)
+{
+    uint32_t h[C];
+#pragma unroll
+    for (int u = 0; u < C; ++u) {
+        const uint32_t j = lane + 32u * u;
+        uint32_t key = GKEY_NONE;
+        if (j < total) {
+            double px, py, pz;
+            int pidx;
+            GridRec<PT>::load(cand, j, px, py, pz, pidx);
+            const double d = dist2_exact(qx, qy, qz, px, py, pz);
+            if (d <= r2) key = (__float_as_uint(__double2float_rd(d)) & ~0xffu) | j;
+        }
+        h[u] = key;
+    }
+    gkey_sort<C>(h);
+    mine = GKEY_NONE;
+    uint32_t m = GKEY_NONE;
+#pragma unroll 1
+    for (int r = 0; r <= k; ++r) {
+        m = __reduce_min_sync(0xffffffffu, h[0]);
+        if ((unsigned)r == lane) mine = m;
+        if (m == GKEY_NONE) break;
+        if ((m & 31u) == lane) {
+#pragma unroll
+            for (int u = 0; u + 1 < C; ++u) h[u] = h[u + 1];
+            h[C - 1] = GKEY_NONE;
+        }
+    }
+    uint32_t nxt = __shfl_down_sync(0xffffffffu, mine, 1);
+    if (lane == 31) nxt = m;                    // k == 32: the 33rd key is only in m
+    amb = __any_sync(0xffffffffu, lane < (unsigned)k && mine != GKEY_NONE && (mine >> 8) == (nxt >> 8));
+    if (lane >= (unsigned)k) mine = GKEY_NONE;
+}
+
+// Exact selection on (d2, index): k rounds of a three-stage warp argmin.  Slow, rare (equal
+// truncated keys: ~0.5 % of the samples of a scanned surface, every sample of a lattice).
+template <typename PT>
+__device__ __forceinline__ void grid_select_exact(const PT *cand, uint32_t total, double qx, double qy,
+                                                  double qz, double r2, int k, unsigned lane,
+                                                  uint32_t &mine)
+{
+    uint32_t taken = 0;
+    mine = GKEY_NONE;
+#pragma unroll 1
+    for (int r = 0; r < k; ++r) {
+        double bd = INFINITY;
+        int bi = IDX_NONE, bu = -1;
+#pragma unroll 1
+        for (int u = 0; lane + 32u * u < total; ++u) {
+            if ((taken >> u) & 1u) continue;
+            double px, py, pz;
+            int pidx;
+            GridRec<PT>::load(cand, lane + 32u * u, px, py, pz, pidx);
+            const double d = dist2_exact(qx, qy, qz, px, py, pz);
+            if (d <= r2 && (bu < 0 || key_less(d, pidx, bd, bi))) { bd = d; bi = pidx; bu = u; }
+        }
+        bool in = bu >= 0;
+        if (!__any_sync(0xffffffffu, in)) break;
+        // every lane takes part in every reduction (no short-circuit around a *_sync call)
+        const uint32_t hi = in ? (uint32_t)__double2hiint(bd) : 0xffffffffu;
+        const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+        in = in && hi == mh;
+        const uint32_t lo = in ? (uint32_t)__double2loint(bd) : 0xffffffffu;
+        const uint32_t ml = __reduce_min_sync(0xffffffffu, lo);
+        in = in && lo == ml;
+        const uint32_t ii = in ? (uint32_t)bi : 0xffffffffu;
+        const uint32_t mi = __reduce_min_sync(0xffffffffu, ii);
+        in = in && ii == mi;
+        const int w = __ffs(__ballot_sync(0xffffffffu, in)) - 1;
+        const uint32_t jw = __shfl_sync(0xffffffffu, (uint32_t)(lane + 32u * (bu < 0 ? 0 : bu)), w);
+        if (lane == (unsigned)w) taken |= 1u << bu;
+        if ((unsigned)r == lane) mine = jw;
+    }
+}
+
+#ifdef PT_STATS
+#define PT_GSTAT(slot, v) do { if (lane == 0) atomicAdd(&g_stats[slot], (unsigned long long)(v)); } while (0)
+#else
+#define PT_GSTAT(slot, v) ((void)0)
+#endif
+// stats slots of the grid kernel: 12 attempts, 13 candidates staged, 14 exact selections,
+// 15 samples handed to the box-pyramid kernels
+
+template <typename PT, int RC, bool TMA>
+__device__ __forceinline__ int grid_stage(const QueryParams &P, const GridTable &T, const uint32_t c[3],
+                                          unsigned lane, PT *cand, uint32_t bar, uint32_t &phase,
+                                          uint32_t &total)
+{
+    constexpr int SIDE = 2 * RC + 1, CELLS = SIDE * SIDE * SIDE, NP = (CELLS + 31) / 32;
+    const uint32_t ncell = 1u << T.level;
+    uint32_t st[NP], ct[NP], mysum = 0;
+    bool dense = false;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int nidx = 32 * p + (int)lane;
+        st[p] = 0; ct[p] = 0;
+        if (nidx < CELLS) {
+            const uint32_t x = c[0] + (uint32_t)(nidx % SIDE) - RC;
+            const uint32_t y = c[1] + (uint32_t)((nidx / SIDE) % SIDE) - RC;
+            const uint32_t z = c[2] + (uint32_t)(nidx / (SIDE * SIDE)) - RC;
+            if (x < ncell && y < ncell && z < ncell)       // unsigned: also rejects "negative" cells
+                grid_lookup(T.buckets, T.cap, x, y, z, st[p], ct[p]);
+            if (ct[p] == 0xffffffffu) { dense = true; ct[p] = 0; }
+            mysum += ct[p];
+        }
+    }
+    uint32_t incl = mysum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += y;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    if (__any_sync(0xffffffffu, dense) || total > (uint32_t)GRID_CAP) return 2;
+    if (total == 0) return 0;
+    uint32_t off = incl - mysum;
+    const PT *pts = reinterpret_cast<const PT *>(P.pts);
+    if (TMA) {
+        // the staging area was read (and the blend tile written) through the generic proxy
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect(bar, total * (uint32_t)sizeof(PT));
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            if (ct[p]) {
+                bulk_g2s(smem_u32(cand + off), pts + st[p], ct[p] * (uint32_t)sizeof(PT), bar);
+                off += ct[p];
+            }
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+    } else {
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            unsigned msk = __ballot_sync(0xffffffffu, ct[p] != 0);
+            const uint32_t myoff = off;
+            off += ct[p];
+            while (msk) {
+                const int e = __ffs(msk) - 1;
+                msk &= msk - 1;
+                const uint32_t s0 = __shfl_sync(0xffffffffu, st[p], e);
+                const uint32_t c0 = __shfl_sync(0xffffffffu, ct[p], e);
+                const uint32_t o0 = __shfl_sync(0xffffffffu, myoff, e);
+                for (uint32_t i = lane; i < c0 * (uint32_t)(sizeof(PT) / 16); i += 32)
+                    ldgsts16(smem_u32(cand + o0) + 16u * i, reinterpret_cast<const char *>(pts + s0) + 16u * i);
+            }
+        }
+        ldgsts_wait_all();
+        __syncwarp();
+    }
+    return 0;
+}
+
+template <typename PT, bool TMA>
+__device__ __forceinline__ void grid_sample(const QueryParams &P, uint32_t s, unsigned lane, PT *cand,
+                                            uint32_t bar, uint32_t &phase, uint32_t *ovf_count,
+                                            uint32_t *ovf_list)
+{
+    const int k = P.k;
+    const double qx = __ldg(P.queries + 3 * (size_t)s);
+    const double qy = __ldg(P.queries + 3 * (size_t)s + 1);
+    const double qz = __ldg(P.queries + 3 * (size_t)s + 2);
+    const double r2 = P.r2_per_query ? __ldg(P.r2_per_query + s) : P.r2;
+    const GridParams &G = P.grid;
+    const double q[3] = {qx, qy, qz};
+    uint32_t c21[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {   // the arithmetic of morton_kernel (pt_build.cu)
+        double t = (q[a] - G.lo[a]) * G.inv_cell21;
+        t = fmin(fmax(t, 0.0), 2097151.0);
+        c21[a] = (uint32_t)t;
+    }
+    const double slack = G.slack + 1.8e-15 * fmax(fmax(fabs(qx), fabs(qy)), fabs(qz));
+
+    uint32_t mine = GKEY_NONE, total = 0;
+    bool done = !(r2 >= 0.0);          // a negative bound admits nothing: the empty answer is final
+    for (int a = 0; a < G.n_attempts && !done; ++a) {
+        const GridTable T = G.tab[G.att_tab[a]];
+        const int rc = G.att_rc[a];
+        const int sh = 21 - T.level;
+        const uint32_t c[3] = {c21[0] >> sh, c21[1] >> sh, c21[2] >> sh};
+        // squared distance from the sample to the nearest face of the searched block that has
+        // cells beyond it (src/Distance.h:27-57 on the block, from inside), minus the margin
+        const double cell = G.cell21 * (double)(1u << sh);
+        const uint32_t ncell = 1u << T.level;
+        double g = INFINITY;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            if (c[ax] + rc + 1 < ncell) g = fmin(g, (G.lo[ax] + (double)(c[ax] + rc + 1) * cell) - q[ax]);
+            if (c[ax] > (uint32_t)rc) g = fmin(g, q[ax] - (G.lo[ax] + (double)(c[ax] - rc) * cell));
+        }
+        g -= slack;
+        const double g2 = g > 0.0 ? __dmul_rd(g, g) : 0.0;
+        PT_GSTAT(12, 1);
+        int rcode;
+        if (rc == 1) rcode = grid_stage<PT, 1, TMA>(P, T, c, lane, cand, bar, phase, total);
+        else rcode = grid_stage<PT, 2, TMA>(P, T, c, lane, cand, bar, phase, total);
+        if (rcode == 2) break;                     // dense bucket / too many candidates
+        PT_GSTAT(13, total);
+        if (total < (uint32_t)k && !(r2 <= g2)) continue;   // cannot fill the list and cannot prove a short one
+        mine = GKEY_NONE;
+        if (total) {
+            bool amb;
+            if (total <= 64u) grid_select<PT, 2>(cand, total, qx, qy, qz, r2, k, lane, mine, amb);
+            else if (total <= 128u) grid_select<PT, 4>(cand, total, qx, qy, qz, r2, k, lane, mine, amb);
+            else grid_select<PT, 8>(cand, total, qx, qy, qz, r2, k, lane, mine, amb);
+            if (amb) {
+                PT_GSTAT(14, 1);
+                grid_select_exact<PT>(cand, total, qx, qy, qz, r2, k, lane, mine);
+            }
+        }
+        const bool has_k = __shfl_sync(0xffffffffu, mine, k - 1) != GKEY_NONE;
+        double bound = r2;
+        if (has_k) {
+            double px, py, pz;
+            int pidx;
+            GridRec<PT>::load(cand, __shfl_sync(0xffffffffu, mine, k - 1) & 0xffu, px, py, pz, pidx);
+            bound = dist2_exact(qx, qy, qz, px, py, pz);
+        }
+        done = bound <= g2;
+    }
+    if (!done) {
+        PT_GSTAT(15, 1);
+        if (lane == 0) ovf_list[atomicAdd(ovf_count, 1u)] = s;
+        return;
+    }
+
+    // ---- outputs: lane r holds the r-th neighbour ------------------------------------------------
+    const bool has = mine != GKEY_NONE;
+    double d = INFINITY;
+    int li = IDX_NONE;
+    if (has) {
+        double px, py, pz;
+        GridRec<PT>::load(cand, mine & 0xffu, px, py, pz, li);
+        d = dist2_exact(qx, qy, qz, px, py, pz);
+    }
+    const int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
+    const bool want_blend = P.rgba_out || P.normal_out;
+    AttrRaw at{0.f, 0.f, 0.f, 0u};
+    if (has && (want_blend || P.cand_out) && P.attrs) at = load_attr(P.attrs + li);
+    if (lane < (unsigned)k) {
+        const size_t o = (size_t)s * k + lane;
+        if (P.idx_out) P.idx_out[o] = gid;
+        if (P.d2_out) P.d2_out[o] = d;
+        if (P.cand_out) store_cand(P.cand_out + o, d, gid, at);
+    }
+    if (!want_blend) return;
+    uint8_t *ro = P.rgba_out ? P.rgba_out + 4 * (size_t)s : nullptr;
+    float *no = P.normal_out ? P.normal_out + 3 * (size_t)s : nullptr;
+    const int cnt = __popc(__ballot_sync(0xffffffffu, has));
+    if (cnt == 0) {
+        if (lane == 0) store_empty_blend(ro, no);
+        return;
+    }
+    // frozen blend: per-neighbour terms in parallel, the sequential sums
+    // one component per lane over a [7][32] tile that reuses the staging area
+    const int mode = __shfl_sync(0xffffffffu, d, 0) == 0.0 ? 1 : 0;
+    const double w = has ? (mode ? (d == 0.0 ? 1.0 : 0.0) : __ddiv_rn(1.0, d)) : 0.0;
+    double *tile = reinterpret_cast<double *>(cand);
+    __syncwarp();                               // every lane has read its winner's record
+    if (has) {
+        tile[0 * 32 + lane] = w;
+        tile[1 * 32 + lane] = __dmul_rn(w, (double)(at.rgba & 0xffu));
+        tile[2 * 32 + lane] = __dmul_rn(w, (double)((at.rgba >> 8) & 0xffu));
+        tile[3 * 32 + lane] = __dmul_rn(w, (double)((at.rgba >> 16) & 0xffu));
+        tile[4 * 32 + lane] = __dmul_rn(w, (double)at.nx);
+        tile[5 * 32 + lane] = __dmul_rn(w, (double)at.ny);
+        tile[6 * 32 + lane] = __dmul_rn(w, (double)at.nz);
+    }
+    __syncwarp();
+    double acc = 0.0;
+    if (lane < 7) {
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, tile[lane * 32 + j]);
+    }
+    double s0 = __shfl_sync(0xffffffffu, acc, 0);
+    if (!(s0 > 0.0 && s0 < INFINITY)) {         // overflowed weights: nearest neighbour only
+        const uint32_t c0 = __shfl_sync(0xffffffffu, at.rgba, 0);
+        const float n0x = __shfl_sync(0xffffffffu, at.nx, 0), n0y = __shfl_sync(0xffffffffu, at.ny, 0),
+                    n0z = __shfl_sync(0xffffffffu, at.nz, 0);
+        const double v[7] = {1.0, (double)(c0 & 0xffu), (double)((c0 >> 8) & 0xffu), (double)((c0 >> 16) & 0xffu),
+                             (double)n0x, (double)n0y, (double)n0z};
+        acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 7; ++a) if (lane == (unsigned)a) acc = v[a];
+        s0 = 1.0;
+    }
+    const double s4 = __shfl_sync(0xffffffffu, acc, 4), s5 = __shfl_sync(0xffffffffu, acc, 5),
+                 s6 = __shfl_sync(0xffffffffu, acc, 6);
+    const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(s4, s4), __dmul_rn(s5, s5)), __dmul_rn(s6, s6)));
+    const double den = lane < 4 ? s0 : len;
+    const double quo = __ddiv_rn(acc, den);
+    const int ci = min(max(__double2int_rz(quo), 0), 255);
+    const int cr = __shfl_sync(0xffffffffu, ci, 1), cg = __shfl_sync(0xffffffffu, ci, 2),
+              cb = __shfl_sync(0xffffffffu, ci, 3);
+    if (lane == 0 && ro) *reinterpret_cast<uchar4 *>(ro) = make_uchar4((unsigned char)cr, (unsigned char)cg, (unsigned char)cb, 255);
+    if (lane >= 4 && lane < 7 && no)
+        no[lane - 4] = (len > 0.0 && len < INFINITY) ? __double2float_rn(quo) : 0.0f;
+}
+
+#ifndef PT_GRID_MIN_BLOCKS
+#define PT_GRID_MIN_BLOCKS 8
+#endif
+template <typename PT, bool TMA>
+__global__ void __launch_bounds__(GRID_WARPS * 32, PT_GRID_MIN_BLOCKS)
+knn_grid_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
+{
+    extern __shared__ __align__(128) unsigned char g_smem[];
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    PT *cand = reinterpret_cast<PT *>(g_smem) + (size_t)wib * GRID_CAP;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(g_smem + sizeof(PT) * GRID_CAP * GRID_WARPS);
+    const uint32_t bar = smem_u32(bars + wib);
+    if (TMA) {
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+    }
+    uint32_t phase = 0;
+    const uint32_t n_warps = gridDim.x * GRID_WARPS;
+    for (uint32_t s = blockIdx.x * GRID_WARPS + wib; s < P.m; s += n_warps)
+        grid_sample<PT, TMA>(P, s, lane, cand, bar, phase, ovf_count, ovf_list);
+}
+
+static inline size_t grid_kernel_smem(size_t rec_bytes)
+{
+    return rec_bytes * GRID_CAP * GRID_WARPS + 8 * GRID_WARPS;
+}
+
+template <typename PT>
+static int launch_grid(const QueryParams &qp, int sm_count, uint32_t *count, uint32_t *list, cudaStream_t s)
+{
+    const size_t smem = grid_kernel_smem(sizeof(PT));
+    const bool tma = opt_grid_tma() != 0;
+    auto kern = tma ? knn_grid_kernel<PT, true> : knn_grid_kernel<PT, false>;
+    if (smem > 48 * 1024)
+        PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRID_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned want = (qp.m + GRID_WARPS - 1) / GRID_WARPS;
+    const unsigned resident = (unsigned)(sm_count * per_sm);
+    kern<<<want < resident ? want : resident, GRID_WARPS * 32, smem, s>>>(qp, count, list);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+}  // namespace pt

@@ -44,12 +44,17 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
         return reinterpret_cast<uint32_t *>(&kq[(j >> 2) * T_THREADS])[j & 3];
     };
 
-    const uint32_t q = blockIdx.x * T_THREADS + tid;
-    bool done = q >= P.m || P.t_levels == 0;
+    // list mode (second stage behind the grid kernel): sample qlist[i], i < *qcount
+    const uint32_t m_eff = P.qlist ? min(*P.qcount, P.m) : P.m;
+    if (blockIdx.x * T_THREADS >= m_eff) return;
+    const uint32_t qi = blockIdx.x * T_THREADS + tid;
+    const bool live = qi < m_eff;
+    const uint32_t q = live ? (P.qlist ? P.qlist[qi] : qi) : 0u;
+    bool done = !live || P.t_levels == 0;
     bool overflow = false;
 
     double qx = 0, qy = 0, qz = 0, r2 = 0;
-    if (q < P.m) {
+    if (live) {
         qx = __ldg(P.queries + 3 * (size_t)q);
         qy = __ldg(P.queries + 3 * (size_t)q + 1);
         qz = __ldg(P.queries + 3 * (size_t)q + 2);
@@ -160,12 +165,12 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     overflow = tr.proof_failed(bound);
 #ifdef PT_STATS
     {
-        unsigned v = (q < P.m && overflow) ? 1u : 0u, w = q < P.m ? 1u : 0u;
+        unsigned v = (live && overflow) ? 1u : 0u, w = live ? 1u : 0u;
         for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); w += __shfl_xor_sync(0xffffffffu, w, o); }
         if (tid == 0) { if (v) atomicAdd(&g_stats[8], (unsigned long long)v); atomicAdd(&g_stats[9], (unsigned long long)w); }
     }
 #endif
-    if (q >= P.m) return;
+    if (!live) return;
     if (overflow) {
         uint32_t slot = atomicAdd(ovf_count, 1u);
         ovf_list[slot] = q;

@@ -136,12 +136,17 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     uint32_t *pqk = reinterpret_cast<uint32_t *>(pdi + TPD_CAP * T_THREADS);     // [TPQ_CAP]
     uint32_t *pqw = pqk + TPQ_CAP * T_THREADS;                                    // [TPQ_CAP]
 
-    const uint32_t q = blockIdx.x * T_THREADS + tid;
-    bool done = q >= P.m || P.t_levels == 0;
+    // list mode (second stage behind the grid kernel, pt_knn_grid.cuh): sample qlist[i], i < *qcount
+    const uint32_t m_eff = P.qlist ? min(*P.qcount, P.m) : P.m;
+    if (blockIdx.x * T_THREADS >= m_eff) return;
+    const uint32_t qi = blockIdx.x * T_THREADS + tid;
+    const bool live = qi < m_eff;
+    const uint32_t q = live ? (P.qlist ? P.qlist[qi] : qi) : 0u;
+    bool done = !live || P.t_levels == 0;
     bool overflow = false;
 
     double qx = 0, qy = 0, qz = 0, r2 = 0;
-    if (q < P.m) {
+    if (live) {
         qx = __ldg(P.queries + 3 * (size_t)q);
         qy = __ldg(P.queries + 3 * (size_t)q + 1);
         qz = __ldg(P.queries + 3 * (size_t)q + 2);
@@ -217,14 +222,14 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     overflow = tr.proof_failed(bound);
 #ifdef PT_STATS
     st_[8] = overflow ? 1 : 0;
-    st_[9] = q < P.m ? 1 : 0;
+    st_[9] = live ? 1 : 0;
     for (int a = 0; a < 12; ++a) {
         unsigned v = st_[a];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (tid == 0 && v) atomicAdd(&g_stats[a], (unsigned long long)v);
     }
 #endif
-    if (q >= P.m) return;
+    if (!live) return;
     if (overflow) {
         uint32_t slot = atomicAdd(ovf_count, 1u);
         ovf_list[slot] = q;

@@ -1,7 +1,7 @@
 // pt_sort.cu -- K2: hand-written LSD radix sort of (64-bit key, 32-bit index) pairs.
 //
 // Sorts the Morton/Hilbert keys of the cloud.  8-bit digits; one
-// pass = three kernels over tiles of 4096 keys:
+// pass = three kernels over tiles of 2048 keys:
 //   rs_hist_kernel    per-tile digit histogram (warp-aggregated shared-memory atomics)
 //                     -> counts[digit][tile]
 //   rs_scan_kernel    per digit, exclusive prefix over the tiles (block scan + carry), digit totals
@@ -22,7 +22,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 #define PT_RS_ROUNDS 8
 #endif
 constexpr int RS_ROUNDS = PT_RS_ROUNDS;             // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;     // 4096
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;     // 2048 keys: 24 KiB staged in shared memory
 constexpr int RS_RADIX = 256;
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -196,11 +196,12 @@ size_t radix_sort_workspace_bytes(uint32_t n)
     return sizeof(uint32_t) * ((size_t)RS_RADIX * num_tiles + 2 * RS_RADIX);
 }
 
-// Sorts pairs by the low `bits` bits of the key.  Ping-pongs between (keys, vals) and
+// Sorts pairs by key bits [first_bit, end_bit) (LSD, 8 bits per pass: the curve keys only need
+// their top bits ordered, pt_build.cu).  Ping-pongs between (keys, vals) and
 // (keys_alt, vals_alt); on return *keys_out / *vals_out point at the buffers holding the result.
 int radix_sort_pairs(unsigned long long *keys, unsigned long long *keys_alt, uint32_t *vals,
-                     uint32_t *vals_alt, uint32_t n, int bits, void *workspace, cudaStream_t s,
-                     unsigned long long **keys_out, uint32_t **vals_out)
+                     uint32_t *vals_alt, uint32_t n, int first_bit, int end_bit, void *workspace,
+                     cudaStream_t s, unsigned long long **keys_out, uint32_t **vals_out)
 {
     *keys_out = keys;
     *vals_out = vals;
@@ -211,7 +212,7 @@ int radix_sort_pairs(unsigned long long *keys, unsigned long long *keys_alt, uin
     uint32_t *bases = totals + RS_RADIX;
     unsigned long long *kin = keys, *kout = keys_alt;
     uint32_t *vin = vals, *vout = vals_alt;
-    for (int shift = 0; shift < bits; shift += 8) {
+    for (int shift = first_bit; shift < end_bit; shift += 8) {
         rs_hist_kernel<<<num_tiles, RS_THREADS, 0, s>>>(kin, n, shift, num_tiles, counts);
         rs_scan_kernel<<<RS_RADIX, RS_THREADS, 0, s>>>(counts, num_tiles, totals);
         rs_base_kernel<<<1, RS_RADIX, 0, s>>>(totals, bases);

@@ -71,12 +71,12 @@ typedef struct pt_build_opts {
 
 typedef struct pt_index_info {
     uint64_t n_points;
-    uint64_t n_leaves;       /* 32-point buckets of the Morton-sorted cloud */
+    uint64_t n_leaves;       /* 32-point buckets of the curve-sorted cloud */
     int      n_levels;       /* box-pyramid levels */
     int      coord_mode;     /* PT_COORD_F32 or PT_COORD_F64 actually used */
     int      device;
-    int      last_fallback_samples; /* samples the last query launch (slot 0) handed to the exact
-                                       warp kernel (queue proof obligation not met); -1 unknown */
+    int      last_fallback_samples; /* samples the last query launch handed to the exact warp
+                                       kernel (queue proof obligation not met); -1 unknown */
     double   bbox_lo[3], bbox_hi[3];
     uint64_t device_bytes;   /* resident after the build */
     float    build_ms;       /* device time of the last build (CUDA events) */
@@ -96,6 +96,11 @@ int pt_index_build(const void *points, size_t n, const pt_build_opts *opts,
                    pt_index **out);
 int pt_index_free(pt_index *index);
 int pt_index_get_info(const pt_index *index, pt_index_info *info);
+
+/* Diagnostics of the last query launch on this index (synchronises the device):
+ * out2[0] = samples re-run by the exact warp kernel (= last_fallback_samples),
+ * out2[1] = samples the grid kernel handed to the box-pyramid kernels. */
+int pt_index_fallback_counts(const pt_index *index, uint32_t out2[2]);
 
 /* radius < 0 or +inf: unbounded k-NN (the reference's mode).  Otherwise only
  * points with d2 <= Distance::transformed_distance(radius) (src/Distance.h:97).
@@ -192,8 +197,11 @@ int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, 
                      int *needs_exchange);
 
 /* Tuning / introspection. */
-/* Options: "knn_variant" (-1 auto [default], 5 scan kernel, 2 thread kernel,
- * 0 warp kernel), "order" (0 Morton, 1 Hilbert, 2 Hilbert + kd refinement [default]),
+/* Options: "knn_variant" (-1 auto [default]: grid kernel first, then scan / thread / warp for
+ * the samples it hands over; 6 grid, 5 scan kernel, 2 thread kernel, 0 warp kernel),
+ * "order" (0 Morton, 1 Hilbert [default], 2 Hilbert + kd refinement: no cell tables),
+ * "grid" (1 build the uniform-grid cell tables [default]), "grid_tma" (1 stage candidate runs
+ * with cp.async.bulk [default], 0 per-lane cp.async), "sort_bits" (ordered key bits, default 48),
  * "sort" (1 hand-written radix sort [default], 0 cub), "host_chunks" (pipeline chunks of the
  * host-buffer API, default 8), "queue_cap" (tests: per-sample traversal queue entries, at most
  * the compiled 12), "verbose", "smem_pad" (diagnosis). */
