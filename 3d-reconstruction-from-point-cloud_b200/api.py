@@ -19,7 +19,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpoints_transfer_b200.so")
+# PT_LIB_NAME selects a diagnosis build of the same library (e.g. the -DPT_STATS one of `make stats`)
+LIB_PATH = os.path.join(_HERE, os.environ.get("PT_LIB_NAME", "libpoints_transfer_b200.so"))
 
 # Byte-for-byte mirror of the reference ``struct Point`` (src/Point.h:1-6), 80 bytes.
 POINT_DTYPE = np.dtype(
@@ -41,15 +42,17 @@ PT_MAX_K = 32
 COORD_AUTO, COORD_F32, COORD_F64 = 0, 1, 2
 SYNTH_HEIGHTFIELD, SYNTH_SKEWED = 0, 1
 
-# Every symbol include/points_transfer.h and include/pt_synth.h declare.
+# Every symbol include/points_transfer.h declares (the drop-in library) ...
 ABI_SYMBOLS = (
     "pt_version", "pt_status_string", "pt_device_count", "pt_index_build", "pt_index_free",
     "pt_index_get_info", "pt_index_fallback_counts", "pt_knn", "pt_transfer", "pt_transfer_slab", "pt_index_build_device", "pt_query_device",
     "pt_merge_device", "pt_halo_route_device", "pt_halo_prepare_device",
     "pt_halo_merge_device", "pt_ghost_check_device", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
-    "pt_synth_cloud_device", "pt_synth_samples_device", "pt_synth_pack_points_device",
-    "pt_synth_pack_queries_device",
 )
+# ... and include/pt_synth.h (bench / test scaffolding, its own library)
+SYNTH_SYMBOLS = ("pt_synth_cloud_device", "pt_synth_samples_device", "pt_synth_pack_points_device",
+                 "pt_synth_pack_queries_device")
+SYNTH_LIB_PATH = os.path.join(_HERE, "libpt_synth_b200.so")
 
 
 class PointsTransferError(RuntimeError):
@@ -133,6 +136,22 @@ def lib():
     L.pt_get_option.restype = i32
     L.pt_get_option.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
     L.pt_kernel_launch_count.restype = ctypes.c_uint64
+    _lib = L
+    return L
+
+
+_synth_lib = None
+
+
+def synth_lib():
+    """The synthetic-workload generators (bench / test scaffolding, libpt_synth_b200.so)."""
+    global _synth_lib
+    if _synth_lib is not None:
+        return _synth_lib
+    if not os.path.exists(SYNTH_LIB_PATH):
+        raise ImportError(f"{SYNTH_LIB_PATH} is missing: run __graft_entry__.build()")
+    L = ctypes.CDLL(SYNTH_LIB_PATH)
+    vp, sz, i32, dbl = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_double
     L.pt_synth_cloud_device.restype = i32
     L.pt_synth_cloud_device.argtypes = [vp, vp, sz, ctypes.POINTER(SynthParams), vp]
     L.pt_synth_samples_device.restype = i32
@@ -141,7 +160,7 @@ def lib():
     L.pt_synth_pack_points_device.argtypes = [vp, vp, sz, vp, vp]
     L.pt_synth_pack_queries_device.restype = i32
     L.pt_synth_pack_queries_device.argtypes = [vp, sz, vp, vp]
-    _lib = L
+    _synth_lib = L
     return L
 
 
@@ -166,7 +185,8 @@ def debug_stats(reset=True):
     buf = (ctypes.c_uint64 * 16)()
     _check(lib().pt_debug_stats(buf, 1 if reset else 0), "pt_debug_stats")
     names = ("expansions", "leaves", "pushes", "pops", "compactions", "heap_inserts", "parked",
-             "warp_rounds", "overflowed", "samples", "warp_drain_iters", "warp_expand_iters")
+             "warp_rounds", "overflowed", "samples", "warp_drain_iters", "warp_expand_iters",
+             "grid_attempts", "grid_candidates", "grid_exact_selects", "grid_handed_over")
     return {n: int(buf[i]) for i, n in enumerate(names)}
 
 

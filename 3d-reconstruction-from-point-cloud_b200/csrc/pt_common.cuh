@@ -83,7 +83,7 @@ constexpr int GRID_MAX_TABLES = 4;
 constexpr int GRID_MAX_ATTEMPTS = 4;
 struct GridTable {
     const GridBucket *buckets;
-    uint32_t          cap;     // slots (linear probing, load <= 1/2)
+    uint32_t          cap;     // slots (even; linear probing in 2-slot groups, load <= 1/3)
     int               level;   // level of the CHILD cells the table resolves
 };
 struct GridParams {
@@ -113,6 +113,7 @@ struct QueryParams {
     GridParams     grid;       // n_tables == 0: no grid
     const uint32_t *qlist;     // optional: the launch answers samples qlist[0 .. *qcount) only
     const uint32_t *qcount;
+    uint32_t        qlist_min; // list mode: do nothing unless *qcount >= qlist_min
     const double  *queries;    // m * 3
     const double  *r2_per_query;
     uint32_t       m;

@@ -105,7 +105,9 @@ grid_insert_kernel(const unsigned long long *keys, const PT *pts, uint32_t n, Gr
     for (int t = 0; t < G.n_tables; ++t) {
         if (ld > G.level[t] - 1) continue;
         const unsigned long long pk = parent_key(c, G.level[t]);
-        uint32_t b = __umulhi(grid_hash(pk), G.cap[t]);
+        // probe order: the two slots of the home group (one aligned 64-byte pair), then the
+        // following groups -- the order grid_lookup (pt_knn_grid.cuh) reads them in
+        uint32_t b = 2u * __umulhi(grid_hash(pk), G.cap[t] >> 1);
         for (;;) {
             GridBucket *B = G.buckets[t] + b;
             const unsigned long long old = atomicCAS(&B->key, ~0ull, pk);
@@ -133,7 +135,7 @@ grid_fill_kernel(const unsigned long long *keys, const PT *pts, uint32_t n, Grid
         const bool child_start = ld_prev <= L, parent_end = ld_next <= L - 1;
         if (!child_start && !parent_end) continue;
         const unsigned long long pk = parent_key(c, L);
-        uint32_t b = __umulhi(grid_hash(pk), G.cap[t]);
+        uint32_t b = 2u * __umulhi(grid_hash(pk), G.cap[t] >> 1);
         GridBucket *B;
         for (;;) {
             B = G.buckets[t] + b;
@@ -198,7 +200,7 @@ static int build_grid_impl(pt_index *ix, const unsigned long long *keys, int low
     size_t total_buckets = 0;
     for (int t = 0; t < GRID_MAX_TABLES && lf - t >= 1; ++t) {
         const int L = lf - t;
-        uint64_t cap = 2 * ix->level_cells[L - 1] + 8;
+        uint64_t cap = (3 * ix->level_cells[L - 1] + 8) & ~1ull;    // load <= 1/3, whole 2-slot groups
         if (cap > 0xfffffff0ull) break;
         G.level[t] = L;
         G.cap[t] = (uint32_t)cap;

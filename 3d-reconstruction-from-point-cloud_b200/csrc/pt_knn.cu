@@ -332,16 +332,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) knn_warp_kernel(const Qu
 template <typename PT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 knn_warp_list_kernel(const QueryParams P, const uint32_t *count, const uint32_t *list,
-                     uint32_t *stat_out, const uint32_t *count_stage1)
+                     uint32_t *stat_out, const uint32_t *count_stage1, uint32_t only_up_to)
 {
     __shared__ float s_lb[WARPS_PER_BLOCK][MAX_W_LEVELS][32];
     const unsigned lane = threadIdx.x & 31;
     const unsigned wib = threadIdx.x >> 5;
-    const uint32_t n = min(*count, P.m);
+    uint32_t n = min(*count, P.m);
     if (stat_out && blockIdx.x == 0 && threadIdx.x == 0) {   // pt_index_info / pt_index_fallback_counts
         stat_out[0] = n;
         stat_out[1] = count_stage1 ? *count_stage1 : 0u;
     }
+    if (n > only_up_to) return;          // a long list belongs to the scan / thread kernel
     for (uint32_t w = blockIdx.x * WARPS_PER_BLOCK + wib; w < n; w += gridDim.x * WARPS_PER_BLOCK)
         warp_query<PT>(P, list[w], lane, s_lb[wib]);
 }
@@ -372,6 +373,8 @@ namespace pt {
 //   grid kernel          --(samples it cannot prove final: list 1)-->
 //   scan / thread kernel --(samples whose queue proof obligation failed: list 2)-->
 //   warp kernel over list 2.
+constexpr uint32_t SHORT_LIST = 2048;   // hand-over lists up to this size go to the warp kernel
+
 template <typename PT>
 static int launch_chain(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s)
 {
@@ -387,15 +390,24 @@ static int launch_chain(pt_index *ix, const QueryParams &qp, int variant, cudaSt
     const bool grid_first = variant == 6;
     if (rc == PT_OK && variant == 6) {
         rc = launch_grid<PT>(qp, ix->sm_count, count1, list1, s);
+        // A short hand-over list is answered by the warp kernel (one warp per sample: a few
+        // samples cost ~30 us there, but a whole ~110 us block latency in the scan / thread
+        // kernels); a long one by the scan / thread kernel in list mode (min_count).
+        if (rc == PT_OK) {
+            knn_warp_list_kernel<PT><<<ix->sm_count * 4, WARPS_PER_BLOCK * 32, 0, s>>>(
+                qp, count1, list1, nullptr, nullptr, SHORT_LIST);
+            count_launch();
+        }
         q2.qlist = list1;
         q2.qcount = count1;
+        q2.qlist_min = SHORT_LIST + 1;
         const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
         variant = (qp.k > 16 || !bounded) ? 5 : 2;
     }
     if (rc == PT_OK) rc = variant == 5 ? launch_scan<PT>(q2, count2, list2, s) : launch_thread<PT>(q2, count2, list2, s);
     if (rc == PT_OK) {
-        knn_warp_list_kernel<PT><<<ix->sm_count * 4, WARPS_PER_BLOCK * 32, 0, s>>>(qp, count2, list2, ix->fallback_word,
-                                                                                         grid_first ? count1 : nullptr);
+        knn_warp_list_kernel<PT><<<ix->sm_count * 4, WARPS_PER_BLOCK * 32, 0, s>>>(
+            qp, count2, list2, ix->fallback_word, grid_first ? count1 : nullptr, 0xffffffffu);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) rc = map_cuda_error(e);
@@ -411,6 +423,7 @@ int launch_query(pt_index *ix, const QueryParams &qp_in, cudaStream_t s)
     QueryParams qp = qp_in;
     qp.qlist = nullptr;
     qp.qcount = nullptr;
+    qp.qlist_min = 0;
     if (ix->n == 0) {
         size_t total = (size_t)qp.m * qp.k;
         empty_result_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(qp);
@@ -422,6 +435,15 @@ int launch_query(pt_index *ix, const QueryParams &qp_in, cudaStream_t s)
     const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
     const bool have_grid = (variant < 0 || variant == 6) && grid_plan(ix, qp.k, qp.r2, qp.grid) > 0;
     if (!have_grid) qp.grid.n_attempts = 0;
+    if (have_grid && verbose()) {
+        fprintf(stderr, "[points_transfer] grid plan k=%d:", qp.k);
+        for (int a = 0; a < qp.grid.n_attempts; ++a) {
+            const int L = qp.grid.tab[qp.grid.att_tab[a]].level;
+            fprintf(stderr, " (level %d, rc %d, occ %.1f)", L, (int)qp.grid.att_rc[a],
+                    (double)ix->n / (double)ix->level_cells[L]);
+        }
+        fprintf(stderr, "\n");
+    }
     if (variant == 6 && !have_grid) variant = -1;
     if (variant < 0) {
         // auto (measured): the grid kernel first whenever the index has

@@ -112,22 +112,27 @@ __device__ __forceinline__ uint32_t grid_hash_q(unsigned long long k)   // = gri
 
 // (start, count) of the run of cell (cx, cy, cz) at the table's level; count 0 when the cell is
 // empty, 0xffffffff when its bucket is unusable (too many points for the 16-bit counts).
+// Slots are probed two at a time (one aligned 64-byte group = one DRAM fetch): the two keys
+// first, then the 24-byte payload of the slot that matched (an L1 hit).
 __device__ __forceinline__ void grid_lookup(const GridBucket *buckets, uint32_t cap, uint32_t cx,
                                             uint32_t cy, uint32_t cz, uint32_t &start, uint32_t &cnt)
 {
     const unsigned long long pkey = (unsigned long long)(cx >> 1) | ((unsigned long long)(cy >> 1) << 21) |
                                     ((unsigned long long)(cz >> 1) << 42);
     const unsigned oct = (cx & 1u) | ((cy & 1u) << 1) | ((cz & 1u) << 2);
-    uint32_t b = __umulhi(grid_hash_q(pkey), cap);
+    const uint32_t ngroups = cap >> 1;
+    uint32_t g = __umulhi(grid_hash_q(pkey), ngroups);
     start = 0;
     cnt = 0;
     for (;;) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(buckets + b);
-        const uint4 a = __ldg(p), c = __ldg(p + 1);
-        const unsigned long long key = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
-        if (key == pkey) {
-            if (((a.w >> (24 + oct)) & 1u) == 0u) return;
-            const unsigned rank = (a.w >> (3 * oct)) & 7u;
+        const unsigned long long *p = reinterpret_cast<const unsigned long long *>(buckets + 2 * (size_t)g);
+        const unsigned long long k0 = __ldg(p), k1 = __ldg(p + 4);
+        if (k0 == pkey || k1 == pkey) {
+            const unsigned long long *b = k0 == pkey ? p : p + 4;
+            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(b + 1));     // start, perm
+            if (((a.y >> (24 + oct)) & 1u) == 0u) return;
+            const uint4 c = __ldg(reinterpret_cast<const uint4 *>(b + 2));     // cum[8]
+            const unsigned rank = (a.y >> (3 * oct)) & 7u;
             const uint32_t total = c.x & 0xffffu;
             if (total == 0xffffu) { cnt = 0xffffffffu; return; }
             const unsigned long long lo = (unsigned long long)c.x | ((unsigned long long)c.y << 32);
@@ -135,12 +140,12 @@ __device__ __forceinline__ void grid_lookup(const GridBucket *buckets, uint32_t 
             const unsigned r1 = rank + 1;
             const uint32_t beg = rank ? (uint32_t)((rank < 4 ? lo >> (16 * rank) : hi >> (16 * (rank - 4))) & 0xffffu) : 0u;
             const uint32_t end = rank < 7 ? (uint32_t)((r1 < 4 ? lo >> (16 * r1) : hi >> (16 * (r1 - 4))) & 0xffffu) : total;
-            start = a.z + beg;
+            start = a.x + beg;
             cnt = end - beg;
             return;
         }
-        if (key == ~0ull) return;
-        if (++b == cap) b = 0;
+        if (k0 == ~0ull || k1 == ~0ull) return;
+        if (++g == ngroups) g = 0;
     }
 }
 
@@ -166,9 +171,12 @@ template <> __device__ __forceinline__ void gkey_sort<8>(uint32_t (&h)[8])   // 
 // Fast selection on truncated keys.  On return lane r < k holds the key of the r-th smallest
 // candidate (GKEY_NONE past the end) and `amb` tells whether some neighbouring pair of the first
 // k + 1 keys shares its truncated distance (then the order / the cut is not proven).
+// Slots [0, carry) and [32, total) of the staging area hold candidates (carry = 32 in the first
+// round of a sample: everything below `total`; later rounds carry the previous winners in the
+// first slots and stage the new window from slot 32 on).
 template <typename PT, int C>
-__device__ __forceinline__ void grid_select(const PT *cand, uint32_t total, double qx, double qy,
-                                            double qz, double r2, int k, unsigned lane,
+__device__ __forceinline__ void grid_select(const PT *cand, uint32_t carry, uint32_t total, double qx,
+                                            double qy, double qz, double r2, int k, unsigned lane,
                                             uint32_t &mine, bool &amb)
 {
     uint32_t h[C];
@@ -176,7 +184,7 @@ __device__ __forceinline__ void grid_select(const PT *cand, uint32_t total, doub
     for (int u = 0; u < C; ++u) {
         const uint32_t j = lane + 32u * u;
         uint32_t key = GKEY_NONE;
-        if (j < total) {
+        if (j < total && (u > 0 || j < carry)) {
             double px, py, pz;
             int pidx;
             GridRec<PT>::load(cand, j, px, py, pz, pidx);
@@ -188,12 +196,12 @@ __device__ __forceinline__ void grid_select(const PT *cand, uint32_t total, doub
     gkey_sort<C>(h);
     mine = GKEY_NONE;
     uint32_t m = GKEY_NONE;
-#pragma unroll 1
+    // k + 1 rounds, no early exit: once the candidates run out every round yields GKEY_NONE
+#pragma unroll 2
     for (int r = 0; r <= k; ++r) {
         m = __reduce_min_sync(0xffffffffu, h[0]);
         if ((unsigned)r == lane) mine = m;
-        if (m == GKEY_NONE) break;
-        if ((m & 31u) == lane) {
+        if ((m & 31u) == lane) {           // the owner pops its head (a GKEY_NONE round pops a GKEY_NONE)
 #pragma unroll
             for (int u = 0; u + 1 < C; ++u) h[u] = h[u + 1];
             h[C - 1] = GKEY_NONE;
@@ -208,9 +216,9 @@ __device__ __forceinline__ void grid_select(const PT *cand, uint32_t total, doub
 // Exact selection on (d2, index): k rounds of a three-stage warp argmin.  Slow, rare (equal
 // truncated keys: ~0.5 % of the samples of a scanned surface, every sample of a lattice).
 template <typename PT>
-__device__ __forceinline__ void grid_select_exact(const PT *cand, uint32_t total, double qx, double qy,
-                                                  double qz, double r2, int k, unsigned lane,
-                                                  uint32_t &mine)
+__device__ __forceinline__ void grid_select_exact(const PT *cand, uint32_t carry, uint32_t total,
+                                                  double qx, double qy, double qz, double r2, int k,
+                                                  unsigned lane, uint32_t &mine)
 {
     uint32_t taken = 0;
     mine = GKEY_NONE;
@@ -220,7 +228,7 @@ __device__ __forceinline__ void grid_select_exact(const PT *cand, uint32_t total
         int bi = IDX_NONE, bu = -1;
 #pragma unroll 1
         for (int u = 0; lane + 32u * u < total; ++u) {
-            if ((taken >> u) & 1u) continue;
+            if (((taken >> u) & 1u) || (u == 0 && lane >= carry)) continue;
             double px, py, pz;
             int pidx;
             GridRec<PT>::load(cand, lane + 32u * u, px, py, pz, pidx);
@@ -254,12 +262,20 @@ __device__ __forceinline__ void grid_select_exact(const PT *cand, uint32_t total
 // stats slots of the grid kernel: 12 attempts, 13 candidates staged, 14 exact selections,
 // 15 samples handed to the box-pyramid kernels
 
+constexpr int GRID_MAX_ROUNDS = 8;    // staging rounds per attempt: 256 + 7 * 224 candidates
+
+// One attempt: look up the (2 RC + 1)^3 block of cells around cell c, stage its points -- in
+// several rounds if they exceed the staging area, the winners so far carried in slots [0, k) --
+// and select the k best.  Returns 0 (lane r's `mine` = slot key of the r-th best, GKEY_NONE past
+// the end), 1 (the block cannot fill the list: try the next attempt) or 2 (hand the sample over).
 template <typename PT, int RC, bool TMA>
-__device__ __forceinline__ int grid_stage(const QueryParams &P, const GridTable &T, const uint32_t c[3],
-                                          unsigned lane, PT *cand, uint32_t bar, uint32_t &phase,
-                                          uint32_t &total)
+__device__ __forceinline__ int grid_attempt(const QueryParams &P, const GridTable &T, const uint32_t c[3],
+                                            double qx, double qy, double qz, double r2, bool short_ok,
+                                            unsigned lane, PT *cand, uint32_t bar, uint32_t &phase,
+                                            uint32_t &mine)
 {
     constexpr int SIDE = 2 * RC + 1, CELLS = SIDE * SIDE * SIDE, NP = (CELLS + 31) / 32;
+    const int k = P.k;
     const uint32_t ncell = 1u << T.level;
     uint32_t st[NP], ct[NP], mysum = 0;
     bool dense = false;
@@ -283,116 +299,138 @@ __device__ __forceinline__ int grid_stage(const QueryParams &P, const GridTable 
         const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= (unsigned)o) incl += y;
     }
-    total = __shfl_sync(0xffffffffu, incl, 31);
-    if (__any_sync(0xffffffffu, dense) || total > (uint32_t)GRID_CAP) return 2;
-    if (total == 0) return 0;
-    uint32_t off = incl - mysum;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (__any_sync(0xffffffffu, dense)) return 2;
+    PT_GSTAT(13, total);
+    if (total < (uint32_t)k && !short_ok) return 1;
+    if (total > (uint32_t)(GRID_CAP + (GRID_MAX_ROUNDS - 1) * (GRID_CAP - 32))) return 2;
+    const uint32_t excl = incl - mysum;       // this lane's runs cover candidates [excl, excl + mysum)
     const PT *pts = reinterpret_cast<const PT *>(P.pts);
-    if (TMA) {
-        // the staging area was read (and the blend tile written) through the generic proxy
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect(bar, total * (uint32_t)sizeof(PT));
-        __syncwarp();
+    mine = GKEY_NONE;
+    uint32_t w0 = 0, carry = 32;
+    while (w0 < total) {
+        const uint32_t base = w0 == 0 ? 0u : 32u;
+        const uint32_t w1 = min(total, w0 + (uint32_t)GRID_CAP - base);
+        // ---- stage candidates [w0, w1) into slots [base, base + w1 - w0) --------------------------
+        if (TMA) {
+            // the staging area was read (and the blend tile written) through the generic proxy
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect(bar, (w1 - w0) * (uint32_t)sizeof(PT));
+            __syncwarp();
+            uint32_t o = excl;
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            if (ct[p]) {
-                bulk_g2s(smem_u32(cand + off), pts + st[p], ct[p] * (uint32_t)sizeof(PT), bar);
-                off += ct[p];
+            for (int p = 0; p < NP; ++p) {
+                const uint32_t lo = max(o, w0), hi = min(o + ct[p], w1);
+                if (lo < hi)
+                    bulk_g2s(smem_u32(cand + base + (lo - w0)), pts + st[p] + (lo - o),
+                             (hi - lo) * (uint32_t)sizeof(PT), bar);
+                o += ct[p];
             }
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-    } else {
-        __syncwarp();
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            __syncwarp();
+            uint32_t o = excl;
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            unsigned msk = __ballot_sync(0xffffffffu, ct[p] != 0);
-            const uint32_t myoff = off;
-            off += ct[p];
-            while (msk) {
-                const int e = __ffs(msk) - 1;
-                msk &= msk - 1;
-                const uint32_t s0 = __shfl_sync(0xffffffffu, st[p], e);
-                const uint32_t c0 = __shfl_sync(0xffffffffu, ct[p], e);
-                const uint32_t o0 = __shfl_sync(0xffffffffu, myoff, e);
-                for (uint32_t i = lane; i < c0 * (uint32_t)(sizeof(PT) / 16); i += 32)
-                    ldgsts16(smem_u32(cand + o0) + 16u * i, reinterpret_cast<const char *>(pts + s0) + 16u * i);
+            for (int p = 0; p < NP; ++p) {
+                const uint32_t lo = max(o, w0), hi = min(o + ct[p], w1);
+                unsigned msk = __ballot_sync(0xffffffffu, lo < hi);
+                while (msk) {
+                    const int e = __ffs(msk) - 1;
+                    msk &= msk - 1;
+                    const uint32_t s0 = __shfl_sync(0xffffffffu, st[p] + (lo - o), e);
+                    const uint32_t c0 = __shfl_sync(0xffffffffu, hi - lo, e);
+                    const uint32_t d0 = __shfl_sync(0xffffffffu, base + (lo - w0), e);
+                    for (uint32_t i = lane; i < c0 * (uint32_t)(sizeof(PT) / 16); i += 32)
+                        ldgsts16(smem_u32(cand + d0) + 16u * i, reinterpret_cast<const char *>(pts + s0) + 16u * i);
+                }
+                o += ct[p];
             }
+            ldgsts_wait_all();
+            __syncwarp();
         }
-        ldgsts_wait_all();
-        __syncwarp();
+        // ---- select -----------------------------------------------------------------------------
+        const uint32_t slots = base + (w1 - w0);
+        bool amb;
+        if (slots <= 64u) grid_select<PT, 2>(cand, carry, slots, qx, qy, qz, r2, k, lane, mine, amb);
+        else if (slots <= 128u) grid_select<PT, 4>(cand, carry, slots, qx, qy, qz, r2, k, lane, mine, amb);
+        else grid_select<PT, 8>(cand, carry, slots, qx, qy, qz, r2, k, lane, mine, amb);
+        if (amb) {
+            PT_GSTAT(14, 1);
+            grid_select_exact<PT>(cand, carry, slots, qx, qy, qz, r2, k, lane, mine);
+        }
+        w0 = w1;
+        if (w0 < total) {       // more to come: the winners so far move to slots [0, count)
+            PT rec{};
+            if (mine != GKEY_NONE) rec = cand[mine & 0xffu];
+            __syncwarp();
+            if (mine != GKEY_NONE) cand[lane] = rec;
+            carry = (uint32_t)__popc(__ballot_sync(0xffffffffu, mine != GKEY_NONE));
+            __syncwarp();
+        }
     }
     return 0;
 }
 
 template <typename PT, bool TMA>
-__device__ __forceinline__ void grid_sample(const QueryParams &P, uint32_t s, unsigned lane, PT *cand,
-                                            uint32_t bar, uint32_t &phase, uint32_t *ovf_count,
-                                            uint32_t *ovf_list)
+__device__ __forceinline__ void grid_sample(const QueryParams &P, uint32_t s, double qx, double qy,
+                                            double qz, unsigned lane, PT *cand, uint32_t bar,
+                                            uint32_t &phase, uint32_t *ovf_count, uint32_t *ovf_list)
 {
     const int k = P.k;
-    const double qx = __ldg(P.queries + 3 * (size_t)s);
-    const double qy = __ldg(P.queries + 3 * (size_t)s + 1);
-    const double qz = __ldg(P.queries + 3 * (size_t)s + 2);
     const double r2 = P.r2_per_query ? __ldg(P.r2_per_query + s) : P.r2;
     const GridParams &G = P.grid;
-    const double q[3] = {qx, qy, qz};
+    // lattice coordinates: the arithmetic of morton_kernel (pt_build.cu); the conversion
+    // saturates, so negative / NaN -> 0 exactly like its fmax(t, 0)
+    const double t[3] = {(qx - G.lo[0]) * G.inv_cell21, (qy - G.lo[1]) * G.inv_cell21,
+                         (qz - G.lo[2]) * G.inv_cell21};
     uint32_t c21[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {   // the arithmetic of morton_kernel (pt_build.cu)
-        double t = (q[a] - G.lo[a]) * G.inv_cell21;
-        t = fmin(fmax(t, 0.0), 2097151.0);
-        c21[a] = (uint32_t)t;
-    }
+    for (int a = 0; a < 3; ++a) c21[a] = min(__double2uint_rz(t[a]), 2097151u);
     const double slack = G.slack + 1.8e-15 * fmax(fmax(fabs(qx), fabs(qy)), fabs(qz));
 
-    uint32_t mine = GKEY_NONE, total = 0;
-    bool done = !(r2 >= 0.0);          // a negative bound admits nothing: the empty answer is final
+    uint32_t mine = GKEY_NONE;
+    double d = INFINITY;                // exact d2 of this lane's neighbour
+    int li = IDX_NONE;
+    bool done = !(r2 >= 0.0);           // a negative bound admits nothing: the empty answer is final
     for (int a = 0; a < G.n_attempts && !done; ++a) {
         const GridTable T = G.tab[G.att_tab[a]];
         const int rc = G.att_rc[a];
         const int sh = 21 - T.level;
         const uint32_t c[3] = {c21[0] >> sh, c21[1] >> sh, c21[2] >> sh};
-        // squared distance from the sample to the nearest face of the searched block that has
-        // cells beyond it (src/Distance.h:27-57 on the block, from inside), minus the margin
-        const double cell = G.cell21 * (double)(1u << sh);
+        // Distance from the sample to the nearest face of the searched block that has cells
+        // beyond it (src/Distance.h:27-57 on the block, seen from inside), in lattice units:
+        // position inside the own cell, bracketed in fp32 and combined with directed rounding so
+        // that the result never exceeds the true distance.
         const uint32_t ncell = 1u << T.level;
-        double g = INFINITY;
+        const float S = (float)(1u << sh), below = (float)rc * S, above = (float)(rc + 1) * S;
+        float gl = INFINITY;
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) {
-            if (c[ax] + rc + 1 < ncell) g = fmin(g, (G.lo[ax] + (double)(c[ax] + rc + 1) * cell) - q[ax]);
-            if (c[ax] > (uint32_t)rc) g = fmin(g, q[ax] - (G.lo[ax] + (double)(c[ax] - rc) * cell));
+            const double f = t[ax] - (double)(c[ax] << sh);
+            const float dl = __fadd_rd(__double2float_rd(f), below);
+            const float du = __fsub_rd(above, __double2float_ru(f));
+            gl = fminf(gl, c[ax] > (uint32_t)rc ? dl : INFINITY);
+            gl = fminf(gl, c[ax] + rc + 1 < ncell ? du : INFINITY);
         }
-        g -= slack;
+        const double g = (double)gl * G.cell21 - slack;
         const double g2 = g > 0.0 ? __dmul_rd(g, g) : 0.0;
         PT_GSTAT(12, 1);
         int rcode;
-        if (rc == 1) rcode = grid_stage<PT, 1, TMA>(P, T, c, lane, cand, bar, phase, total);
-        else rcode = grid_stage<PT, 2, TMA>(P, T, c, lane, cand, bar, phase, total);
+        if (rc == 1) rcode = grid_attempt<PT, 1, TMA>(P, T, c, qx, qy, qz, r2, r2 <= g2, lane, cand, bar, phase, mine);
+        else rcode = grid_attempt<PT, 2, TMA>(P, T, c, qx, qy, qz, r2, r2 <= g2, lane, cand, bar, phase, mine);
         if (rcode == 2) break;                     // dense bucket / too many candidates
-        PT_GSTAT(13, total);
-        if (total < (uint32_t)k && !(r2 <= g2)) continue;   // cannot fill the list and cannot prove a short one
-        mine = GKEY_NONE;
-        if (total) {
-            bool amb;
-            if (total <= 64u) grid_select<PT, 2>(cand, total, qx, qy, qz, r2, k, lane, mine, amb);
-            else if (total <= 128u) grid_select<PT, 4>(cand, total, qx, qy, qz, r2, k, lane, mine, amb);
-            else grid_select<PT, 8>(cand, total, qx, qy, qz, r2, k, lane, mine, amb);
-            if (amb) {
-                PT_GSTAT(14, 1);
-                grid_select_exact<PT>(cand, total, qx, qy, qz, r2, k, lane, mine);
-            }
-        }
-        const bool has_k = __shfl_sync(0xffffffffu, mine, k - 1) != GKEY_NONE;
-        double bound = r2;
-        if (has_k) {
+        if (rcode == 1) continue;                  // cannot fill the list and cannot prove a short one
+        d = INFINITY;
+        li = IDX_NONE;
+        if (mine != GKEY_NONE) {
             double px, py, pz;
-            int pidx;
-            GridRec<PT>::load(cand, __shfl_sync(0xffffffffu, mine, k - 1) & 0xffu, px, py, pz, pidx);
-            bound = dist2_exact(qx, qy, qz, px, py, pz);
+            GridRec<PT>::load(cand, mine & 0xffu, px, py, pz, li);
+            d = dist2_exact(qx, qy, qz, px, py, pz);
         }
-        done = bound <= g2;
+        const double kth = __shfl_sync(0xffffffffu, d, k - 1);     // +inf while the list is short
+        done = fmin(kth, r2) <= g2;
     }
     if (!done) {
         PT_GSTAT(15, 1);
@@ -402,13 +440,6 @@ __device__ __forceinline__ void grid_sample(const QueryParams &P, uint32_t s, un
 
     // ---- outputs: lane r holds the r-th neighbour ------------------------------------------------
     const bool has = mine != GKEY_NONE;
-    double d = INFINITY;
-    int li = IDX_NONE;
-    if (has) {
-        double px, py, pz;
-        GridRec<PT>::load(cand, mine & 0xffu, px, py, pz, li);
-        d = dist2_exact(qx, qy, qz, px, py, pz);
-    }
     const int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
     const bool want_blend = P.rgba_out || P.normal_out;
     AttrRaw at{0.f, 0.f, 0.f, 0u};
@@ -433,20 +464,27 @@ __device__ __forceinline__ void grid_sample(const QueryParams &P, uint32_t s, un
     const double w = has ? (mode ? (d == 0.0 ? 1.0 : 0.0) : __ddiv_rn(1.0, d)) : 0.0;
     double *tile = reinterpret_cast<double *>(cand);
     __syncwarp();                               // every lane has read its winner's record
-    if (has) {
-        tile[0 * 32 + lane] = w;
-        tile[1 * 32 + lane] = __dmul_rn(w, (double)(at.rgba & 0xffu));
-        tile[2 * 32 + lane] = __dmul_rn(w, (double)((at.rgba >> 8) & 0xffu));
-        tile[3 * 32 + lane] = __dmul_rn(w, (double)((at.rgba >> 16) & 0xffu));
-        tile[4 * 32 + lane] = __dmul_rn(w, (double)at.nx);
-        tile[5 * 32 + lane] = __dmul_rn(w, (double)at.ny);
-        tile[6 * 32 + lane] = __dmul_rn(w, (double)at.nz);
-    }
+    tile[0 * 32 + lane] = w;                    // lanes past the list write zeros that are never read
+    tile[1 * 32 + lane] = __dmul_rn(w, (double)(at.rgba & 0xffu));
+    tile[2 * 32 + lane] = __dmul_rn(w, (double)((at.rgba >> 8) & 0xffu));
+    tile[3 * 32 + lane] = __dmul_rn(w, (double)((at.rgba >> 16) & 0xffu));
+    tile[4 * 32 + lane] = __dmul_rn(w, (double)at.nx);
+    tile[5 * 32 + lane] = __dmul_rn(w, (double)at.ny);
+    tile[6 * 32 + lane] = __dmul_rn(w, (double)at.nz);
     __syncwarp();
     double acc = 0.0;
     if (lane < 7) {
+        const double *row = tile + lane * 32;
+        int j = 0;
 #pragma unroll 1
-        for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, tile[lane * 32 + j]);
+        for (; j + 4 <= cnt; j += 4) {
+            acc = __dadd_rn(acc, row[j]);
+            acc = __dadd_rn(acc, row[j + 1]);
+            acc = __dadd_rn(acc, row[j + 2]);
+            acc = __dadd_rn(acc, row[j + 3]);
+        }
+#pragma unroll 1
+        for (; j < cnt; ++j) acc = __dadd_rn(acc, row[j]);
     }
     double s0 = __shfl_sync(0xffffffffu, acc, 0);
     if (!(s0 > 0.0 && s0 < INFINITY)) {         // overflowed weights: nearest neighbour only
@@ -491,8 +529,22 @@ knn_grid_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     }
     uint32_t phase = 0;
     const uint32_t n_warps = gridDim.x * GRID_WARPS;
-    for (uint32_t s = blockIdx.x * GRID_WARPS + wib; s < P.m; s += n_warps)
-        grid_sample<PT, TMA>(P, s, lane, cand, bar, phase, ovf_count, ovf_list);
+    uint32_t s = blockIdx.x * GRID_WARPS + wib;
+    if (s >= P.m) return;
+    double qx = __ldg(P.queries + 3 * (size_t)s), qy = __ldg(P.queries + 3 * (size_t)s + 1),
+           qz = __ldg(P.queries + 3 * (size_t)s + 2);
+    while (s < P.m) {
+        // the next sample's coordinates are fetched while this one is answered
+        const uint32_t sn = s + n_warps;
+        double nx = 0.0, ny = 0.0, nz = 0.0;
+        if (sn < P.m) {
+            nx = __ldg(P.queries + 3 * (size_t)sn);
+            ny = __ldg(P.queries + 3 * (size_t)sn + 1);
+            nz = __ldg(P.queries + 3 * (size_t)sn + 2);
+        }
+        grid_sample<PT, TMA>(P, s, qx, qy, qz, lane, cand, bar, phase, ovf_count, ovf_list);
+        s = sn; qx = nx; qy = ny; qz = nz;
+    }
 }
 
 static inline size_t grid_kernel_smem(size_t rec_bytes)

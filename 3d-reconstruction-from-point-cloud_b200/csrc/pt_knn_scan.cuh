@@ -45,7 +45,8 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     };
 
     // list mode (second stage behind the grid kernel): sample qlist[i], i < *qcount
-    const uint32_t m_eff = P.qlist ? min(*P.qcount, P.m) : P.m;
+    uint32_t m_eff = P.qlist ? min(*P.qcount, P.m) : P.m;
+    if (P.qlist && m_eff < P.qlist_min) m_eff = 0;       // short lists are the warp kernel's
     if (blockIdx.x * T_THREADS >= m_eff) return;
     const uint32_t qi = blockIdx.x * T_THREADS + tid;
     const bool live = qi < m_eff;

@@ -1,10 +1,23 @@
 // pt_synth.cu -- synthetic clouds / mesh samples for tests and bench (include/pt_synth.h;
 // SURVEY.md section 8 row M1).  Counter-based RNG: Philox4x32-10, key = seed, counter = global
 // point index, so any slab can be regenerated independently on any rank.
+//
+// Bench / test scaffolding: built into its OWN library (libpt_synth_b200.so), not into the
+// drop-in libpoints_transfer_b200.so, and its launches are not counted as product kernels.
 #include <cmath>
+#include <cstdint>
+#include <cstdio>
 
-#include "pt_common.cuh"
+#include <cuda_runtime.h>
+
 #include "pt_synth.h"
+
+#define PT_CUDA(call)                                                       \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) return e__ == cudaErrorNoDevice ? PT_ERR_NO_DEVICE : PT_ERR_CUDA; \
+    } while (0)
+static inline void count_launch() {}
 
 namespace pt {
 

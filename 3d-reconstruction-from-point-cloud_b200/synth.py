@@ -1,7 +1,7 @@
 """Synthetic workloads of BASELINE.json's configs.
 
 The reference ships no sample data, so clouds and mesh samples are generated on the device by
-``pt_synth_*`` (csrc/pt_synth.cu): a noisy heightfield scan over ``[0, L]^2`` or a skewed
+``pt_synth_*`` (csrc/pt_synth.cu, built into the bench-only libpt_synth_b200.so): a noisy heightfield scan over ``[0, L]^2`` or a skewed
 cluster cloud, Philox4x32-10 keyed by ``seed`` with the global point index as counter.
 """
 import ctypes
@@ -59,7 +59,7 @@ def cloud_device(n, seed, u0=0.0, u1=L_DOMAIN, v0=0.0, v1=L_DOMAIN, kind=api.SYN
     sp = api.SynthParams(kind=int(kind), seed=int(seed), first_index=int(first_index),
                          u0=u0, u1=u1, v0=v0, v1=v1, sigma=sigma)
     with torch.cuda.device(device):
-        api._check(api.lib().pt_synth_cloud_device(api._tptr(pos), api._tptr(attrs), n,
+        api._check(api.synth_lib().pt_synth_cloud_device(api._tptr(pos), api._tptr(attrs), n,
                                                    ctypes.byref(sp), api._stream_ptr()),
                    "pt_synth_cloud_device")
     return pos, attrs
@@ -71,7 +71,7 @@ def samples_device(gu, gv, u0=0.0, u1=L_DOMAIN, v0=0.0, v1=L_DOMAIN, center=Fals
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     q = torch.empty((gu * gv, 3), dtype=torch.float64, device=device)
     with torch.cuda.device(device):
-        api._check(api.lib().pt_synth_samples_device(api._tptr(q), gu, gv, u0, u1, v0, v1,
+        api._check(api.synth_lib().pt_synth_samples_device(api._tptr(q), gu, gv, u0, u1, v0, v1,
                                                      1 if center else 0, api._stream_ptr()),
                    "pt_synth_samples_device")
     return q
@@ -83,7 +83,7 @@ def points_to_host(pos, attrs):
     n = pos.shape[0]
     raw = torch.empty((n, 80), dtype=torch.uint8, device=pos.device)
     with torch.cuda.device(pos.device):
-        api._check(api.lib().pt_synth_pack_points_device(api._tptr(pos), api._tptr(attrs), n,
+        api._check(api.synth_lib().pt_synth_pack_points_device(api._tptr(pos), api._tptr(attrs), n,
                                                          api._tptr(raw), api._stream_ptr()),
                    "pt_synth_pack_points_device")
     return raw.cpu().numpy().view(api.POINT_DTYPE).reshape(-1)
@@ -94,7 +94,7 @@ def queries_to_host(q, pinned=False):
     m = q.shape[0]
     raw = torch.empty((m, 80), dtype=torch.uint8, device=q.device)
     with torch.cuda.device(q.device):
-        api._check(api.lib().pt_synth_pack_queries_device(api._tptr(q), m, api._tptr(raw),
+        api._check(api.synth_lib().pt_synth_pack_queries_device(api._tptr(q), m, api._tptr(raw),
                                                           api._stream_ptr()),
                    "pt_synth_pack_queries_device")
     if pinned:

@@ -264,13 +264,15 @@ static void tight_box(const pto_point **p, int64_t b, int64_t e, double lo[3], d
         }
 }
 
+/* Nodes come from one array reserved up front (a tree over n points has fewer than 2n nodes;
+ * untouched pages cost nothing), so subtrees can be built by concurrent OpenMP tasks: the only
+ * shared state is this counter. */
 static int32_t new_node(pto_kdtree *t)
 {
-    if (t->n_nodes == t->cap_nodes) {
-        t->cap_nodes = t->cap_nodes ? t->cap_nodes * 2 : 1024;
-        t->nodes = (kd_node *)realloc(t->nodes, (size_t)t->cap_nodes * sizeof(kd_node));
-    }
-    return (int32_t)t->n_nodes++;
+    int64_t id;
+#pragma omp atomic capture
+    id = t->n_nodes++;
+    return (int32_t)id;
 }
 
 /* Builds the subtree over ptrs[b,e) whose loose box is (blo,bhi) and tight box
@@ -278,6 +280,7 @@ static int32_t new_node(pto_kdtree *t)
  * side of the loose box at its midpoint; if the tight box is degenerate there,
  * use the longest tight side; slide the cut onto the tight box if all points
  * fall on one side. */
+#define PTO_TASK_MIN 65536
 static int32_t build_rec(pto_kdtree *t, int64_t b, int64_t e, const double blo[3],
                          const double bhi[3], const double tlo[3], const double thi[3])
 {
@@ -331,8 +334,16 @@ static int32_t build_rec(pto_kdtree *t, int64_t b, int64_t e, const double blo[3
         nd->lower_low = llo[cd]; nd->lower_high = lhi[cd];
         nd->upper_low = ulo[cd]; nd->upper_high = uhi[cd];
     }
-    int32_t lo_id = build_rec(t, b, mid, lblo, lbhi, llo, lhi);
-    int32_t up_id = build_rec(t, mid, e, ublo, ubhi, ulo, uhi);
+    int32_t lo_id, up_id;
+    if (e - b >= PTO_TASK_MIN) {      /* big subtrees: one task each (disjoint ranges of ptrs[]) */
+#pragma omp task shared(lo_id) firstprivate(t, b, mid, lblo, lbhi, llo, lhi)
+        lo_id = build_rec(t, b, mid, lblo, lbhi, llo, lhi);
+        up_id = build_rec(t, mid, e, ublo, ubhi, ulo, uhi);
+#pragma omp taskwait
+    } else {
+        lo_id = build_rec(t, b, mid, lblo, lbhi, llo, lhi);
+        up_id = build_rec(t, mid, e, ublo, ubhi, ulo, uhi);
+    }
     t->nodes[id].lower = lo_id;
     t->nodes[id].upper = up_id;
     return id;
@@ -346,11 +357,20 @@ pto_kdtree *pto_kdtree_build(const pto_point *pts, int64_t n, int bucket_size)
     t->pts = (pto_point *)malloc((size_t)(n > 0 ? n : 1) * sizeof(pto_point));
     t->ptrs = (const pto_point **)malloc((size_t)(n > 0 ? n : 1) * sizeof(*t->ptrs));
     if (!t->pts || !t->ptrs) { pto_kdtree_free(t); return NULL; }
-    memcpy(t->pts, pts, (size_t)n * sizeof(pto_point));
-    for (int64_t i = 0; i < n; ++i) t->ptrs[i] = &t->pts[i];
+    t->cap_nodes = 2 * (n > 0 ? n : 1) + 16;
+    t->nodes = (kd_node *)malloc((size_t)t->cap_nodes * sizeof(kd_node));
+    if (!t->nodes) { pto_kdtree_free(t); return NULL; }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) { t->pts[i] = pts[i]; t->ptrs[i] = &t->pts[i]; }
     if (n > 0) {
         tight_box(t->ptrs, 0, n, t->bb_lo, t->bb_hi);
+#pragma omp parallel
+#pragma omp single
         build_rec(t, 0, n, t->bb_lo, t->bb_hi, t->bb_lo, t->bb_hi);
+    }
+    {   /* give the untouched tail of the reservation back */
+        kd_node *shrunk = (kd_node *)realloc(t->nodes, (size_t)(t->n_nodes > 0 ? t->n_nodes : 1) * sizeof(kd_node));
+        if (shrunk) { t->nodes = shrunk; t->cap_nodes = t->n_nodes; }
     }
     return t;
 }

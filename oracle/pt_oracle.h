@@ -100,6 +100,14 @@ int64_t pto_reference_face_loop(const pto_kdtree *t, const pto_point *vertices,
 
 int pto_max_threads(void);
 
+/* Host restatement of the synthetic workload generators (pt_synth_host.c): the clouds and mesh
+ * samples of BASELINE.json's configs on the host cores, without any CUDA code (bench.py's
+ * reference arm).  kind: 0 heightfield scan, 1 skewed clusters.  Returns 0. */
+int pto_synth_cloud(pto_point *out, int64_t n, int kind, uint64_t seed, uint64_t first_index,
+                    double u0, double u1, double v0, double v1, double sigma, int nthreads);
+int pto_synth_samples(pto_point *out, int64_t gu, int64_t gv, double u0, double u1, double v0,
+                      double v1, int center);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ def build(force=False):
     """Compile the C restatement (gcc, oracle/Makefile)."""
     if force or not os.path.exists(_LIB_PATH) or (
         os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f))
-                                          for f in ("pt_oracle.c", "pt_oracle.h"))
+                                          for f in ("pt_oracle.c", "pt_synth_host.c", "pt_oracle.h"))
     ):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
                        stdout=subprocess.DEVNULL)
@@ -98,6 +98,11 @@ def lib():
         L.pto_reference_face_loop.restype = i64
         L.pto_reference_face_loop.argtypes = [vp, vp, vp, i64, i32, i32]
         L.pto_max_threads.restype = i32
+        u64 = ctypes.c_uint64
+        L.pto_synth_cloud.restype = i32
+        L.pto_synth_cloud.argtypes = [vp, i64, i32, u64, u64, dbl, dbl, dbl, dbl, dbl, i32]
+        L.pto_synth_samples.restype = i32
+        L.pto_synth_samples.argtypes = [vp, i64, i64, dbl, dbl, dbl, dbl, i32]
         _lib = L
     return _lib
 
@@ -205,3 +210,21 @@ class KdTree:
 
 def max_threads():
     return lib().pto_max_threads()
+
+
+def synth_cloud(n, seed, kind=0, u0=0.0, u1=1000.0, v0=0.0, v1=1000.0, sigma=0.01, first_index=0,
+                nthreads=0):
+    """Host restatement of the device cloud generator (pt_synth_host.c): ``n`` Point records."""
+    out = np.empty(int(n), dtype=POINT_DTYPE)
+    rc = lib().pto_synth_cloud(_ptr(out), int(n), int(kind), int(seed), int(first_index), u0, u1,
+                               v0, v1, sigma, nthreads)
+    assert rc == 0, rc
+    return out
+
+
+def synth_samples(gu, gv, u0=0.0, u1=1000.0, v0=0.0, v1=1000.0, center=False):
+    """gu x gv mesh samples on the noise-free surface (row-major, v outer) as Point records."""
+    out = np.empty(int(gu) * int(gv), dtype=POINT_DTYPE)
+    rc = lib().pto_synth_samples(_ptr(out), int(gu), int(gv), u0, u1, v0, v1, 1 if center else 0)
+    assert rc == 0, rc
+    return out
