@@ -47,7 +47,8 @@ ABI_SYMBOLS = (
     "pt_version", "pt_status_string", "pt_device_count", "pt_index_build", "pt_index_free",
     "pt_index_get_info", "pt_index_fallback_counts", "pt_knn", "pt_transfer", "pt_transfer_slab", "pt_index_build_device", "pt_query_device",
     "pt_merge_device", "pt_halo_route_device", "pt_halo_prepare_device",
-    "pt_halo_merge_device", "pt_ghost_check_device", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
+    "pt_halo_merge_device", "pt_ghost_check_device", "pt_route_samples_device",
+    "pt_scatter_rows_device", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
 )
 # ... and include/pt_synth.h (bench / test scaffolding, its own library)
 SYNTH_SYMBOLS = ("pt_synth_cloud_device", "pt_synth_samples_device", "pt_synth_pack_points_device",
@@ -131,6 +132,10 @@ def lib():
     L.pt_halo_merge_device.argtypes = [vp, vp, vp, vp, u32, i32, vp, vp, vp, vp, vp]
     L.pt_ghost_check_device.restype = i32
     L.pt_ghost_check_device.argtypes = [vp, vp, sz, i32, dbl, vp, i32, i32, dbl, vp, vp]
+    L.pt_route_samples_device.restype = i32
+    L.pt_route_samples_device.argtypes = [vp, sz, vp, i32, u32, vp, vp, vp, vp, vp]
+    L.pt_scatter_rows_device.restype = i32
+    L.pt_scatter_rows_device.argtypes = [vp, vp, sz, u32, vp, vp]
     L.pt_set_option.restype = i32
     L.pt_set_option.argtypes = [ctypes.c_char_p, i32]
     L.pt_get_option.restype = i32

@@ -369,6 +369,25 @@ int pt_halo_route_device(const double *queries_xyz, const pt_cand *own_cand, siz
                              (cudaStream_t)stream);
 }
 
+int pt_route_samples_device(const double *queries_xyz, size_t m, const double *cuts, int n_ranks,
+                            uint32_t cap, double *send, int32_t *sel, uint32_t *counts,
+                            uint32_t *overflow_flag, void *stream)
+{
+    if ((m && !queries_xyz) || !cuts || !send || !sel || !counts || !overflow_flag || m > 0xfffffff0ull)
+        return PT_ERR_INVALID_ARG;
+    if (pt_device_count() == 0) return PT_ERR_NO_DEVICE;
+    return launch_route_samples(queries_xyz, (uint32_t)m, cuts, n_ranks, cap, send, sel, counts,
+                                overflow_flag, (cudaStream_t)stream);
+}
+
+int pt_scatter_rows_device(const void *src, const int32_t *sel, size_t rows, uint32_t row_bytes,
+                           void *dst, void *stream)
+{
+    if ((rows && (!src || !sel || !dst)) || rows > 0xfffffff0ull) return PT_ERR_INVALID_ARG;
+    if (pt_device_count() == 0) return PT_ERR_NO_DEVICE;
+    return launch_scatter_rows(src, sel, (uint32_t)rows, row_bytes, dst, (cudaStream_t)stream);
+}
+
 int pt_ghost_check_device(const double *queries_xyz, const double *d2, size_t m, int k,
                           double radius, const double *boxes, int n_ranks, int self, double halo,
                           uint32_t *flag, void *stream)

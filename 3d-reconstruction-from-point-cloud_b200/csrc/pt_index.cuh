@@ -99,6 +99,12 @@ int launch_halo_merge(pt_cand *own, const pt_cand *back, const int32_t *sel, con
                       uint32_t cap, int k, int32_t *idx_out, double *d2_out, uint8_t *rgba_out,
                       float *normal_out, cudaStream_t s);
 
+int launch_route_samples(const double *q, uint32_t m, const double *cuts, int n_ranks, uint32_t cap,
+                         double *send, int32_t *sel, uint32_t *counts, uint32_t *overflow_flag,
+                         cudaStream_t s);
+int launch_scatter_rows(const void *src, const int32_t *sel, uint32_t rows, uint32_t row_bytes, void *dst,
+                        cudaStream_t s);
+
 size_t radix_sort_workspace_bytes(uint32_t n);
 int radix_sort_pairs(unsigned long long *keys, unsigned long long *keys_alt, uint32_t *vals,
                      uint32_t *vals_alt, uint32_t n, int first_bit, int end_bit, void *workspace,

@@ -666,6 +666,75 @@ ghost_check_kernel(const double *q, const double *d2, uint32_t m, int k, double 
     if (__any_sync(0xffffffffu, viol) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
+// ---- sample routing for slab-sharded clouds --------------------------------
+// Samples arrive in arbitrary order on any rank; the slab that owns a sample is the one whose
+// x-range [cuts[r], cuts[r + 1]) holds it.  Fixed-capacity blocks per destination, so the
+// all_to_all that follows needs no host synchronisation: row = (x, y, z, +inf) -- the 4th word
+// is the per-query squared bound of pt_query_device -- and rows past a block's count keep the
+// NaN bound the caller memsets (0xff), which every query kernel answers with an empty list.
+__global__ void __launch_bounds__(256)
+route_samples_kernel(const double *q, uint32_t m, const double *cuts, int n_ranks, uint32_t cap,
+                     double *send, int32_t *sel, uint32_t *counts, uint32_t *overflow_flag)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m) return;
+    const double x = q[3 * (size_t)s];
+    int lo = 0, hi = n_ranks - 1;            // last r with cuts[r] <= x (cuts[0] = -inf)
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (cuts[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t pos = atomicAdd(&counts[lo], 1u);
+    if (pos >= cap) { atomicOr(overflow_flag, 1u); return; }
+    double *row = send + ((size_t)lo * cap + pos) * 4;
+    row[0] = x; row[1] = q[3 * (size_t)s + 1]; row[2] = q[3 * (size_t)s + 2]; row[3] = INFINITY;
+    sel[(size_t)lo * cap + pos] = (int32_t)s;
+}
+
+// dst[sel[t]] = src[t] for every row t with sel[t] >= 0; rows are row_words 4-byte words.
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const uint32_t *src, const int32_t *sel, uint32_t rows, uint32_t row_words,
+                    uint32_t *dst)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * row_words) return;
+    const uint32_t t = (uint32_t)(i / row_words), w = (uint32_t)(i % row_words);
+    const int32_t d = sel[t];
+    if (d >= 0) dst[(size_t)d * row_words + w] = src[i];
+}
+
+int launch_route_samples(const double *q, uint32_t m, const double *cuts, int n_ranks, uint32_t cap,
+                         double *send, int32_t *sel, uint32_t *counts, uint32_t *overflow_flag,
+                         cudaStream_t s)
+{
+    if (n_ranks < 1 || n_ranks > 4096 || cap == 0) return PT_ERR_INVALID_ARG;
+    const size_t rows = (size_t)n_ranks * cap;
+    PT_CUDA(cudaMemsetAsync(send, 0xff, sizeof(double) * 4 * rows, s));       // NaN rows
+    PT_CUDA(cudaMemsetAsync(sel, 0xff, sizeof(int32_t) * rows, s));           // -1
+    PT_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * n_ranks, s));
+    PT_CUDA(cudaMemsetAsync(overflow_flag, 0, sizeof(uint32_t), s));
+    if (m) {
+        route_samples_kernel<<<(m + 255) / 256, 256, 0, s>>>(q, m, cuts, n_ranks, cap, send, sel, counts,
+                                                            overflow_flag);
+        count_launch();
+    }
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int launch_scatter_rows(const void *src, const int32_t *sel, uint32_t rows, uint32_t row_bytes, void *dst,
+                        cudaStream_t s)
+{
+    if (row_bytes == 0 || row_bytes % 4 != 0) return PT_ERR_INVALID_ARG;
+    const size_t total = (size_t)rows * (row_bytes / 4);
+    if (total == 0) return PT_OK;
+    scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        (const uint32_t *)src, sel, rows, row_bytes / 4, (uint32_t *)dst);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
 int launch_ghost_check(const double *q, const double *d2, uint32_t m, int k, double r2,
                        const double *boxes, int n_ranks, int self, double halo, uint32_t *flag,
                        cudaStream_t s)

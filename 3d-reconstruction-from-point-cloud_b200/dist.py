@@ -138,6 +138,38 @@ class CudaSlabEngine:
         return out
 
 
+def route_samples(q, cuts, cap, out=None, stream=None):
+    """pt_route_samples_device: q float64 [m,3] CUDA, cuts float64 [R+1] CUDA (-inf first, +inf
+    last).  Returns (send [R,cap,4] f64, sel [R,cap] i32, counts [R] i32, overflow [1] i32);
+    ``out`` = a previous result to reuse the buffers."""
+    from . import api
+    R = cuts.numel() - 1
+    dev = q.device
+    if out is None:
+        out = (torch.empty((R, cap, 4), dtype=torch.float64, device=dev),
+               torch.empty((R, cap), dtype=torch.int32, device=dev),
+               torch.empty((R,), dtype=torch.int32, device=dev),
+               torch.empty((1,), dtype=torch.int32, device=dev))
+    send, sel, counts, overflow = out
+    with torch.cuda.device(dev):
+        api._check(api.lib().pt_route_samples_device(
+            api._tptr(q), q.shape[0], api._tptr(cuts), R, int(cap), api._tptr(send), api._tptr(sel),
+            api._tptr(counts), api._tptr(overflow), api._stream_ptr(stream)), "pt_route_samples_device")
+    return out
+
+
+def scatter_rows(src, sel, dst, stream=None):
+    """pt_scatter_rows_device: dst[sel[t]] = src[t] for sel[t] >= 0 (row-major CUDA tensors)."""
+    from . import api
+    rows = sel.numel()
+    row_bytes = src.element_size() * (src.numel() // max(rows, 1))
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype
+    with torch.cuda.device(src.device):
+        api._check(api.lib().pt_scatter_rows_device(api._tptr(src), api._tptr(sel), rows, row_bytes,
+                                                    api._tptr(dst), api._stream_ptr(stream)),
+                   "pt_scatter_rows_device")
+
+
 def cand_d2(cand):
     """k-th ... view the squared distances of pt_cand records: cand uint8 [..., 32] -> f64 [...]."""
     return cand[..., :8].contiguous().view(torch.float64).squeeze(-1)

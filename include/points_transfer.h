@@ -176,6 +176,20 @@ int pt_halo_merge_device(pt_cand *own_cand, const pt_cand *back, const int32_t *
                          const uint32_t *count, uint32_t cap, int k, int32_t *idx_out,
                          double *d2_out, uint8_t *rgba_out, float *normal_out, void *stream);
 
+/* Sample routing of a slab-sharded cloud: samples arrive in arbitrary order; slab r owns the
+ * samples with cuts[r] <= x < cuts[r + 1] (cuts: n_ranks + 1 doubles in DEVICE memory, cuts[0]
+ * = -inf, cuts[n_ranks] = +inf).  Per destination a block of `cap` rows of 4 doubles (x, y, z,
+ * +inf = per-query squared bound of pt_query_device); unused rows are NaN (answered with empty
+ * lists), sel[r * cap + j] = index of the sample in that row or -1, counts[r] = rows used,
+ * *overflow_flag = 1 when a block did not fit (nothing is dropped silently: enlarge cap). */
+int pt_route_samples_device(const double *queries_xyz, size_t m, const double *cuts, int n_ranks,
+                            uint32_t cap, double *send, int32_t *sel, uint32_t *counts,
+                            uint32_t *overflow_flag, void *stream);
+/* The way back: dst[sel[t]] = src[t] for every row t with sel[t] >= 0 (rows of row_bytes
+ * bytes, a multiple of 4). */
+int pt_scatter_rows_device(const void *src, const int32_t *sel, size_t rows, uint32_t row_bytes,
+                           void *dst, void *stream);
+
 /* Ghost-zone check for slab indexes that also hold the other slabs' points within `halo` of
  * this slab's box: ORs 1 into *flag if some sample's k-th-neighbour ball (d2[m*k], bounded by
  * radius) reaches another slab's box and may leave the ghost zone, i.e. the step needs the
