@@ -12,3 +12,4 @@ from .api import (  # noqa: F401
 )
 from . import synth  # noqa: F401
 from . import dist  # noqa: F401,E402
+from . import sharded  # noqa: F401,E402

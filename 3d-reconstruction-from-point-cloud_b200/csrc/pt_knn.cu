@@ -539,6 +539,7 @@ halo_route_kernel(const double *q, const pt_cand *own, uint32_t m, int k, double
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= m) return;
     const double x = q[3 * (size_t)s], y = q[3 * (size_t)s + 1], z = q[3 * (size_t)s + 2];
+    if (x != x) return;                       // NaN row: an unused slot of a routing block
     const double bound = fmin(own[(size_t)s * k + (k - 1)].d2, r2);   // +inf while the list is short
     for (int r = 0; r < n_ranks; ++r) {
         if (r == self) continue;
@@ -643,7 +644,7 @@ ghost_check_kernel(const double *q, const double *d2, uint32_t m, int k, double 
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     bool viol = false;
-    if (s < m) {
+    if (s < m && q[3 * (size_t)s] == q[3 * (size_t)s]) {     // NaN row: an unused slot of a routing block
         const double x = q[3 * (size_t)s], y = q[3 * (size_t)s + 1], z = q[3 * (size_t)s + 2];
         const double bound = fmin(d2[(size_t)s * k + (k - 1)], r2);
         const double *ob = boxes + 6 * self;

@@ -145,6 +145,22 @@ def route_samples(q, cuts, cap, out=None, stream=None):
     from . import api
     R = cuts.numel() - 1
     dev = q.device
+    if not q.is_cuda:      # host-logic tests over gloo: the same contract in torch ops
+        send = torch.full((R, cap, 4), float("nan"), dtype=torch.float64)
+        sel = torch.full((R, cap), -1, dtype=torch.int32)
+        counts = torch.zeros((R,), dtype=torch.int32)
+        overflow = torch.zeros((1,), dtype=torch.int32)
+        owner = torch.bucketize(q[:, 0].contiguous(), cuts[1:-1].contiguous(), right=True)
+        for r in range(R):
+            ids = torch.nonzero(owner == r).view(-1)
+            counts[r] = ids.numel()
+            if ids.numel() > cap:
+                overflow[0] = 1
+                ids = ids[:cap]
+            send[r, :ids.numel(), :3] = q[ids]
+            send[r, :ids.numel(), 3] = float("inf")
+            sel[r, :ids.numel()] = ids.to(torch.int32)
+        return send, sel, counts, overflow
     if out is None:
         out = (torch.empty((R, cap, 4), dtype=torch.float64, device=dev),
                torch.empty((R, cap), dtype=torch.int32, device=dev),
@@ -162,6 +178,10 @@ def scatter_rows(src, sel, dst, stream=None):
     """pt_scatter_rows_device: dst[sel[t]] = src[t] for sel[t] >= 0 (row-major CUDA tensors)."""
     from . import api
     rows = sel.numel()
+    if not src.is_cuda:
+        valid = sel.view(-1) >= 0
+        dst[sel.view(-1)[valid].long()] = src.view(rows, -1)[valid].view((-1,) + tuple(dst.shape[1:]))
+        return
     row_bytes = src.element_size() * (src.numel() // max(rows, 1))
     assert src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype
     with torch.cuda.device(src.device):
@@ -257,6 +277,11 @@ class SlabTransfer:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         dev = engine.device
         self.halo = None if halo is None else float(halo)
+        if halo is not None and own_box is None:
+            # the engine's bbox already includes the ghost points: the ghost-zone test would be
+            # evaluated against an inflated box and declare inexact results final
+            raise ValueError("SlabTransfer(halo=...) needs own_box, the box of the slab's OWN points "
+                             "(the one exchange_ghosts was called with)")
         if own_box is not None:
             box = own_box.to(torch.float64).to(dev)
         else:
@@ -292,15 +317,16 @@ class SlabTransfer:
             self.cap *= 2
         return not bad
 
-    def _transfer_ghost(self, q, k, radius, want_d2, validate=True):
+    def _transfer_ghost(self, q, k, radius, want_d2, validate=True, r2pq=None):
         """Owner-only step on the ghost-augmented index + the check that no sample's k-th
         neighbour ball leaves the ghost zone.  Returns None when the step must be redone with
         the exchange (only possible with validate=True; otherwise validate() reports it)."""
         eng = self.engine
+        kw = {} if r2pq is None else {"radius2_per_query": r2pq}
         try:
-            _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True, want_cand=False)
+            _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True, want_cand=False, **kw)
         except TypeError:            # engines without the want_cand switch (test stand-ins)
-            _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True)
+            _, out = eng.query(q, k, radius=radius, outputs=True, want_d2=True, **kw)
         if q.shape[0] and hasattr(eng, "ghost_check"):       # one small kernel on the CUDA engine
             if not validate:
                 # deferred check: the kernel ORs (atomically, so chunks on several streams may
@@ -340,11 +366,12 @@ class SlabTransfer:
         dist.all_reduce(viol, op=dist.ReduceOp.MAX, group=self.group)
         return None if int(viol.item()) else out
 
-    def _transfer_fast(self, q, k, radius, want_d2, validate=True):
+    def _transfer_fast(self, q, k, radius, want_d2, validate=True, r2pq=None):
         """Fixed-capacity exchange on the CUDA engine: route kernel -> all_to_all -> bounded halo
         search -> all_to_all -> per-peer merge kernels; one deferred overflow check at the end."""
         eng, R, cap = self.engine, self.world, self.cap
-        own, out = eng.query(q, k, radius=radius, outputs=True, want_d2=want_d2)
+        own, out = eng.query(q, k, radius=radius, outputs=True, want_d2=want_d2,
+                             **({} if r2pq is None else {"radius2_per_query": r2pq}))
         h = eng.halo_buffers(R, cap, k)
         h["flag"].zero_()
         eng.halo_route(q, own, k, radius, self.boxes6, self.rank, cap, h)
@@ -450,7 +477,7 @@ class SlabTransfer:
             out[name].copy_(r[name], non_blocking=True)
         torch.cuda.synchronize(dev)
 
-    def transfer(self, q, k, radius=None, want_d2=False, validate=True):
+    def transfer(self, q, k, radius=None, want_d2=False, validate=True, r2pq=None):
         """q float64 [m,3] on the engine's device (samples owned by this rank).
         Returns dict(idx int32 [m,k] global ids, rgba uint8 [m,4], normal float32 [m,3][, d2]).
         ``validate=False`` (CUDA engine only) skips the per-step overflow agreement, making the
@@ -458,19 +485,20 @@ class SlabTransfer:
         eng, dev, R = self.engine, self.device, self.world
         m = q.shape[0]
         if R > 1 and self.halo is not None:
-            out = self._transfer_ghost(q, k, radius, want_d2, validate)
+            out = self._transfer_ghost(q, k, radius, want_d2, validate, r2pq)
             if out is not None:
                 self.stats = {"crossing": 0, "sent": 0, "received": 0, "path": "ghost-zone",
                               "halo": self.halo}
                 return out
         if R > 1 and getattr(eng, "fast", False):
-            out = self._transfer_fast(q, k, radius, want_d2, validate)
+            out = self._transfer_fast(q, k, radius, want_d2, validate, r2pq)
             if out is not None:
                 self.stats = {"crossing": None, "sent": None, "received": None, "path": "fast",
                               "cap": self.cap}
                 return out
         r2 = float("inf") if (radius is None or radius < 0) else float(radius) * float(radius)
-        own, out = eng.query(q, k, radius=radius, outputs=True, want_d2=want_d2)   # [m, k, 32]
+        own, out = eng.query(q, k, radius=radius, outputs=True, want_d2=want_d2,
+                             **({} if r2pq is None else {"radius2_per_query": r2pq}))   # [m, k, 32]
         if R == 1:
             self.stats = {"crossing": 0, "sent": 0, "received": 0}
             return out
