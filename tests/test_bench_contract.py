@@ -29,3 +29,31 @@ def test_reference_arm_prints_the_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+    assert cb["same_config"] is True and cb["points"] == d["config"]["points"]
+
+
+def test_reference_arm_loads_no_cuda_library():
+    """The reference arm must be self-contained: it generates the workload on the host
+    (oracle/pt_synth_host.c) and never dlopens the product's CUDA libraries."""
+    code = ("import sys, os; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', "
+            "'--workload', 'cfg1']; sys.path.insert(0, %r); import runpy; runpy.run_path(%r, run_name='__main__'); "
+            "maps = open('/proc/self/maps').read(); "
+            "assert 'libpoints_transfer_b200' not in maps and 'libpt_synth_b200' not in maps, 'CUDA library loaded'; "
+            "assert 'libpt_oracle' in maps" % (ROOT, os.path.join(ROOT, "bench.py")))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+
+
+def test_both_arms_emit_the_same_config():
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    import __graft_entry__ as ge
+    pkg = ge.package()
+    w = pkg.synth.CONFIGS["cfg2"]
+    a = bench.make_config(w, w.n_points, w.gu, w.gv, w.k, 1)
+    assert a["points"] == 50_000_000 and a["samples"] == 200_704 and a["k"] == 16
+    assert bench.pick_workload(type("A", (), {"workload": "auto"})(), 1) == "cfg2"
+    assert bench.pick_workload(type("A", (), {"workload": "auto"})(), 2) == "cfg3"
+    assert bench.pick_workload(type("A", (), {"workload": "auto"})(), 4) == "cfg3"
+    assert bench.pick_workload(type("A", (), {"workload": "auto"})(), 8) == "cfg4"

@@ -393,3 +393,25 @@ def test_baseline_config_shapes_vs_oracle(cfg, n, g, k, pkg, pto, torch_cuda):
     if cfg == "cfg5":
         short = (ref_idx < 0).any(axis=1).mean()
         assert 0.05 < short < 1.0      # the radius bound really bites on the sparse part
+
+
+def test_host_generator_matches_device(pkg, pto, torch_cuda):
+    """oracle/pt_synth_host.c restates the device generators (csrc/pt_synth.cu) for the CPU arm of
+    bench.py: same Philox streams and formulas; only the libm differs, so after the rounding to
+    fp32 at most a few coordinates per million may be one fp32 ulp apart."""
+    for cfg in ("cfg2", "cfg5"):
+        w = pkg.synth.CONFIGS[cfg]
+        n = 400_000
+        pos, attrs = pkg.synth.cloud_device(n, w.seed, kind=w.kind, sigma=w.sigma, first_index=12345)
+        D = pkg.synth.points_to_host(pos, attrs)
+        H = pto.synth_cloud(n, w.seed, kind=w.kind, sigma=w.sigma, first_index=12345)
+        diff = np.abs(D["ver"] - H["ver"])
+        ulp = np.spacing(np.abs(D["ver"]).astype(np.float32)).astype(np.float64)
+        assert np.all(diff <= ulp)
+        assert (diff > 0).mean() < 1e-4
+        assert (np.abs(D["normal"] - H["normal"]) > 1e-6).mean() < 1e-4
+        assert (D["color"] != H["color"]).mean() < 1e-4
+    q = pkg.synth.samples_device(300, 200, center=True)
+    Qd = pkg.synth.queries_to_host(q)
+    Qh = pto.synth_samples(300, 200, center=True)
+    assert (np.abs(Qd["ver"] - Qh["ver"]) > 0).mean() < 1e-4
