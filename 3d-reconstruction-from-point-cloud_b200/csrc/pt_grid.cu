@@ -192,10 +192,12 @@ static int build_grid_impl(pt_index *ix, const unsigned long long *keys, int low
         if (l <= max_level) cells += h_hist[l];
         ix->level_cells[l] = l <= max_level ? cells : 0;
     }
-    // finest table: the finest level that still averages >= 1.8 points per occupied cell
+    // finest table: the finest level that still averages >= 4 points per occupied cell.  (A finer
+    // one would only serve k < 8 a little better and costs most of the build: its bucket count
+    // grows 4-8x per level.)
     int lf = 1;
     for (int l = 1; l <= max_level; ++l)
-        if ((double)n / (double)ix->level_cells[l] >= 1.8) lf = l;
+        if ((double)n / (double)ix->level_cells[l] >= 4.0) lf = l;
     GridBuildTables G{};
     size_t total_buckets = 0;
     for (int t = 0; t < GRID_MAX_TABLES && lf - t >= 1; ++t) {
