@@ -378,13 +378,11 @@ constexpr uint32_t SHORT_LIST = 2048;   // hand-over lists up to this size go to
 template <typename PT>
 static int launch_chain(pt_index *ix, const QueryParams &qp, int variant, cudaStream_t s)
 {
-    const size_t words = (size_t)qp.m + 4;
     uint32_t *ws = nullptr;
-    PT_TRY(pool_alloc((void **)&ws, sizeof(uint32_t) * 2 * words, s));
-    uint32_t *count1 = ws, *list1 = ws + 4, *count2 = ws + words, *list2 = count2 + 4;
+    PT_TRY(pool_alloc((void **)&ws, sizeof(uint32_t) * (8 + 2 * (size_t)qp.m), s));
+    uint32_t *count1 = ws, *count2 = ws + 4, *list1 = ws + 8, *list2 = list1 + qp.m;
     int rc = PT_OK;
-    cudaError_t e = cudaMemsetAsync(count1, 0, 4 * sizeof(uint32_t), s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(count2, 0, 4 * sizeof(uint32_t), s);
+    cudaError_t e = cudaMemsetAsync(ws, 0, 8 * sizeof(uint32_t), s);     // both counters at once
     if (e != cudaSuccess) rc = map_cuda_error(e);
     QueryParams q2 = qp;
     const bool grid_first = variant == 6;
