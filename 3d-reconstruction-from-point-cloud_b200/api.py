@@ -45,7 +45,7 @@ SYNTH_HEIGHTFIELD, SYNTH_SKEWED = 0, 1
 # Every symbol include/points_transfer.h declares (the drop-in library) ...
 ABI_SYMBOLS = (
     "pt_version", "pt_status_string", "pt_device_count", "pt_index_build", "pt_index_free",
-    "pt_index_get_info", "pt_index_fallback_counts", "pt_knn", "pt_transfer", "pt_transfer_slab", "pt_index_build_device", "pt_query_device",
+    "pt_index_get_info", "pt_index_fallback_counts", "pt_knn", "pt_transfer", "pt_texture_render", "pt_transfer_slab", "pt_index_build_device", "pt_query_device",
     "pt_merge_device", "pt_halo_route_device", "pt_halo_prepare_device",
     "pt_halo_merge_device", "pt_ghost_check_device", "pt_route_samples_device",
     "pt_scatter_rows_device", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
@@ -75,6 +75,11 @@ class IndexInfo(ctypes.Structure):
                 ("device_bytes", ctypes.c_uint64), ("build_ms", ctypes.c_float),
                 ("last_query_ms", ctypes.c_float), ("last_h2d_ms", ctypes.c_float),
                 ("last_d2h_ms", ctypes.c_float)]
+
+
+class TextureStats(ctypes.Structure):
+    _fields_ = [("triangles", ctypes.c_uint64), ("inside_points", ctypes.c_uint64),
+                ("knn_ms", ctypes.c_float), ("draw_ms", ctypes.c_float), ("pad_ms", ctypes.c_float)]
 
 
 class SynthParams(ctypes.Structure):
@@ -114,6 +119,8 @@ def lib():
     L.pt_knn.argtypes = [vp, vp, sz, i32, dbl, vp, vp]
     L.pt_transfer.restype = i32
     L.pt_transfer.argtypes = [vp, vp, sz, i32, dbl, vp, vp, vp, vp]
+    L.pt_texture_render.restype = i32
+    L.pt_texture_render.argtypes = [vp, vp, sz, vp, sz, i32, dbl, i32, i32, vp, ctypes.POINTER(TextureStats)]
     L.pt_transfer_slab.restype = i32
     L.pt_transfer_slab.argtypes = [vp, vp, i32, sz, i32, dbl, vp, i32, i32, dbl, vp, vp, vp, vp,
                                    ctypes.POINTER(i32)]
@@ -349,6 +356,20 @@ class Tree:
                                  _np_ptr(out["rgba"]), _np_ptr(out["normal"])), "pt_transfer")
         return out
 
+
+    def texture(self, vertices, faces, k=20, resolution=8192, radius=None, pad=True):
+        """The reference's output image (src/pointsTransfer.cpp:462-611): per-face transfer of the
+        cloud's colours into the mesh's UV space.  vertices: Point records (position, U, V,
+        colour), faces: int32 [F,3].  Returns (bgra uint8 [res,res,4] as cv::Mat CV_8UC4, stats)."""
+        v = _as_points(vertices, "vertices")
+        f = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
+        img = np.empty((resolution, resolution, 4), dtype=np.uint8)
+        st = TextureStats()
+        _check(lib().pt_texture_render(self._h, _np_ptr(v), v.shape[0], _np_ptr(f), f.shape[0], int(k),
+                                       _radius(radius), int(resolution), 1 if pad else 0, _np_ptr(img),
+                                       ctypes.byref(st)), "pt_texture_render")
+        return img, {"triangles": int(st.triangles), "inside_points": int(st.inside_points),
+                     "knn_ms": st.knn_ms, "draw_ms": st.draw_ms, "pad_ms": st.pad_ms}
 
     def transfer_slab(self, queries_ptr, queries_are_xyz, m, k, radius, boxes6, rank, halo,
                       idx_ptr, rgba_ptr, normal_ptr, d2_ptr=None):

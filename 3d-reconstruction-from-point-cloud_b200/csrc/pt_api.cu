@@ -17,6 +17,7 @@ static std::atomic<int> g_sort{1};    // 1 hand-written radix sort (default), 0 
 static std::atomic<int> g_order{1};   // 0 Morton, 1 Hilbert (default), 2 Hilbert + kd refinement (no cell tables)
 static std::atomic<int> g_grid{1};        // build the uniform-grid cell tables (pt_grid.cu)
 static std::atomic<int> g_grid_tma{1};    // stage candidate runs with cp.async.bulk (0: per-lane cp.async)
+static std::atomic<int> g_pool_keep_mb{2048};   // temporaries kept cached in the library's pool after a build / free
 static std::atomic<int> g_sort_bits{48};  // ordered key bits, from the top (cells contiguous down to level 16)
 
 bool verbose()
@@ -48,6 +49,7 @@ int opt_sort() { return g_sort.load(); }
 int opt_grid() { return g_grid.load(); }
 int opt_grid_tma() { return g_grid_tma.load(); }
 int opt_sort_bits() { return g_sort_bits.load(); }
+size_t opt_pool_keep_bytes() { return (size_t)g_pool_keep_mb.load() << 20; }
 static std::atomic<int> g_host_chunks{8};   // host-buffer API: pipeline chunks per call (one stream each, up to 16)
 int opt_host_chunks() { return g_host_chunks.load(); }
 static std::atomic<int> g_queue_cap{1 << 20};   // tests: shrink the per-sample queue (exactness under spilling)
@@ -68,6 +70,7 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "grid")) { g_grid.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "grid_tma")) { g_grid_tma.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { g_sort_bits.store(value); return PT_OK; }
+    if (!strcmp(name, "pool_keep_mb")) { g_pool_keep_mb.store(value < 0 ? 0 : value); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { g_queue_cap.store(value < 2 ? 2 : value); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { g_host_chunks.store(value < 1 ? 1 : (value > 64 ? 64 : value)); return PT_OK; }
@@ -83,6 +86,7 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "grid")) { *value = g_grid.load(); return PT_OK; }
     if (!strcmp(name, "grid_tma")) { *value = g_grid_tma.load(); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { *value = g_sort_bits.load(); return PT_OK; }
+    if (!strcmp(name, "pool_keep_mb")) { *value = g_pool_keep_mb.load(); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { *value = g_smem_pad.load(); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { *value = g_queue_cap.load(); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { *value = g_host_chunks.load(); return PT_OK; }
@@ -143,8 +147,8 @@ static void destroy_index(pt_index *ix)
     if (ix->boxes) cudaFreeAsync(ix->boxes, ix->stream);
     if (ix->grid_mem) cudaFreeAsync(ix->grid_mem, ix->stream);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    pool_trim(ix->device, (size_t)2 << 30);   // at most 2 GiB stay cached for the next build
-    cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->fallback_word);
+    pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" (default 2 GiB) stays cached for the next build
+    cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->fallback_word); cudaFree(ix->inv_perm);
     cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out);
     for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
     for (auto &e : ix->cev) if (e) cudaEventDestroy(e);

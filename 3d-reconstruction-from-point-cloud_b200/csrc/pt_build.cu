@@ -636,7 +636,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     cudaFreeAsync(arena, s);
     arena_guard.p = nullptr;
     cudaStreamSynchronize(s);
-    pool_trim(ix->device, (size_t)2 << 30);   // at most 2 GiB of temporaries stay cached for the next build
+    pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" (default 2 GiB) of temporaries stays cached
     ix->device_bytes = sizeof(Out) * n_pad + sizeof(Box) * total + ix->grid_bytes +
                        (ix->attrs ? sizeof(pt_attr) * (size_t)n : 0) +
                        (ix->ids ? sizeof(int32_t) * (size_t)n : 0);

@@ -21,6 +21,7 @@ struct pt_index {
     pt::GridParams grid{};                // tables of this index (n_tables == 0: none)
     uint64_t     level_cells[22]{};       // occupied cells per lattice level (0: not counted)
     uint32_t    *fallback_word = nullptr; // device: samples the last launch handed to the warp kernel
+    uint32_t    *inv_perm = nullptr;      // original index -> position in pts (pt_texture.cu, built on demand)
     uint64_t     device_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t  ev[4]{};
@@ -120,6 +121,7 @@ int  opt_queue_cap();
 int  opt_grid();
 int  opt_grid_tma();
 int  opt_sort_bits();
+size_t opt_pool_keep_bytes();
 int  debug_stats(unsigned long long *out16, int reset);
 
 }  // namespace pt

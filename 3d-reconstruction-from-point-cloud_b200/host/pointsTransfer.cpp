@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "points_transfer.h"
+#include "pt_png.h"
 #include "pt_point.h"
 
 using ptb::Point;
@@ -239,17 +240,26 @@ int main(int argc, char **argv)
     int K = 20;             // src/pointsTransfer.cpp:128
     double radius = -1.0;   // unbounded, as the reference
     int device = -1;
-    std::string out_name = "transferred.ply";
+    int resolution = 8192;  // src/pointsTransfer.cpp:129
+    std::string out_name = "texture.png";          // src/pointsTransfer.cpp:613
+    std::string ply_name;                          // optional extra: the per-vertex blend as a PLY
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "-k" && i + 1 < argc) K = atoi(argv[++i]);
         else if (a == "-r" && i + 1 < argc) radius = atof(argv[++i]);
         else if (a == "-o" && i + 1 < argc) out_name = argv[++i];
+        else if (a == "-p" && i + 1 < argc) ply_name = argv[++i];
+        else if (a == "-R" && i + 1 < argc) resolution = atoi(argv[++i]);
         else if (a == "-d" && i + 1 < argc) device = atoi(argv[++i]);
         else pos_args.push_back(a);
     }
     if (pos_args.size() < 2) {
         std::cout << usage_str << std::endl;
+        return 0;
+    }
+    if (K < 1 || K > PT_MAX_K || resolution < 1 || resolution > 32768) {
+        // like every error path of the reference: a message, exit code 0
+        std::cerr << "-k must be 1.." << PT_MAX_K << " and -R 1..32768" << std::endl;
         return 0;
     }
     const std::string pc_file_name = pos_args[0], mesh_file_name = pos_args[1];
@@ -311,23 +321,37 @@ int main(int argc, char **argv)
     std::cout << "Read mesh faces: " << task_timer.time() << " seconds" << std::endl;
     task_timer.reset();
 
-    // one batched call over the unique vertices replaces the 3*F per-corner searches (:465-479)
+    // The face loop (:462-585) and the texture post-process (:593-611) in one call: ONE batched
+    // search over the unique vertices replaces the 3*F per-corner searches (:465-479), then the
+    // per-face projection / Delaunay / rasterisation kernels and the dilate + gutter.
     const size_t m = vertices.size();
-    std::vector<int32_t> idx(m * (size_t)K);
-    std::vector<uint8_t> rgba(m * 4);
-    std::vector<float> normal(m * 3);
-    rc = pt_transfer(index, vertices.data(), m, K, radius, idx.data(), nullptr, rgba.data(), normal.data());
+    std::vector<uint8_t> texture((size_t)resolution * resolution * 4);
+    pt_texture_stats ts;
+    memset(&ts, 0, sizeof ts);
+    rc = pt_texture_render(index, vertices.data(), m, faces.data(), faces.size() / 3, K, radius, resolution, 1,
+                           texture.data(), &ts);
     if (rc != PT_OK) {
-        std::cerr << "pt_transfer failed: " << pt_status_string(rc) << std::endl;
+        std::cerr << "pt_texture_render failed: " << pt_status_string(rc) << std::endl;
         pt_index_free(index);
         return 0;
     }
-    std::cout << "Neighbor search total time: " << task_timer.time() << " seconds" << std::endl;
     task_timer.reset();
-    std::cout << "Draw triangles total time: " << 0 << " seconds" << std::endl;
+    std::cout << "Neighbor search total time: " << ts.knn_ms * 1e-3 << " seconds" << std::endl;
+    std::cout << "Draw triangles total time: " << (ts.draw_ms + ts.pad_ms) * 1e-3 << " seconds" << std::endl;
 
-    {
-        std::ofstream out(out_name);
+    if (!ptb::write_png_bgra(out_name.c_str(), texture.data(), resolution, resolution))
+        std::cerr << "Cannot write " << out_name << std::endl;
+    if (!ply_name.empty()) {
+        // extra (not in the reference): the fused per-vertex colour / normal blend of pt_transfer
+        std::vector<uint8_t> rgba(m * 4);
+        std::vector<float> normal(m * 3);
+        rc = pt_transfer(index, vertices.data(), m, K, radius, nullptr, nullptr, rgba.data(), normal.data());
+        if (rc != PT_OK) {
+            std::cerr << "pt_transfer failed: " << pt_status_string(rc) << std::endl;
+            pt_index_free(index);
+            return 0;
+        }
+        std::ofstream out(ply_name);
         out << "ply\nformat ascii 1.0\nelement vertex " << m << "\n"
             << "property float x\nproperty float y\nproperty float z\n"
             << "property float nx\nproperty float ny\nproperty float nz\n"

@@ -13,6 +13,8 @@
  *                       src/Distance.h:6-11, radius transform src/Distance.h:97.
  *   pt_transfer      <- the per-sample transfer loop src/pointsTransfer.cpp:
  *                       465-479 + the colour blend semantics of :95-103.
+ *   pt_texture_render<- the face loop body after the searches and the texture
+ *                       post-process, src/pointsTransfer.cpp:484-611 + draw_triangle :66-107.
  *   pt_index_free    <- `tree` going out of scope at src/pointsTransfer.cpp:626.
  *
  * Records are the reference's own 80-byte AoS `struct Point`
@@ -113,6 +115,25 @@ int pt_knn(pt_index *index, const void *queries, size_t m, int k, double radius,
 int pt_transfer(pt_index *index, const void *queries, size_t m, int k,
                 double radius, int32_t *idx_out, double *d2_out,
                 uint8_t *rgba_out, float *normal_out);
+
+/* Everything the reference does after the neighbour search, for a whole mesh
+ * (src/pointsTransfer.cpp:462-611): per face the union of the K nearest cloud points of its
+ * corners, projection onto the face plane + in-triangle filter (:484-537), Delaunay
+ * sub-triangulation with barycentric UVs (:539-581), rasterisation of every sub-triangle with
+ * interpolated colours (draw_triangle, :66-107) and, with pad != 0, the 25x25 dilate + gutter
+ * (:593-611).  vertices: n_vertices Point records (position, U, V, colour are read); faces:
+ * 3 int32 vertex indices per face (n_faces < 2^24); bgra_out: resolution * resolution * 4 bytes
+ * in HOST memory, row 0 first, byte order B G R A as cv::Mat CV_8UC4 -- what the reference hands
+ * to cv::imwrite("texture.png").  Pixels nobody draws are 0 (the reference leaves them
+ * uninitialised); the reference's out-of-bounds row / column writes are skipped. */
+typedef struct pt_texture_stats {
+    uint64_t triangles;      /* sub-triangles drawn */
+    uint64_t inside_points;  /* neighbours kept by the in-triangle filter, all faces */
+    float    knn_ms, draw_ms, pad_ms;   /* device time of the three stages */
+} pt_texture_stats;
+int pt_texture_render(pt_index *index, const void *vertices, size_t n_vertices,
+                      const int32_t *faces, size_t n_faces, int k, double radius,
+                      int resolution, int pad, uint8_t *bgra_out, pt_texture_stats *stats);
 
 /* Device-buffer API: same operations with inputs/outputs already resident in
  * HBM on the index's device (bench `value`, multi-GPU slabs).  `stream` is a
@@ -216,6 +237,8 @@ int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, 
  * "order" (0 Morton, 1 Hilbert [default], 2 Hilbert + kd refinement: no cell tables),
  * "grid" (1 build the uniform-grid cell tables [default]), "grid_tma" (1 stage candidate runs
  * with cp.async.bulk [default], 0 per-lane cp.async), "sort_bits" (ordered key bits, default 48),
+ * "pool_keep_mb" (build temporaries kept cached in the library's private memory pool after a
+ * build or a free, default 2048: a rebuild of a larger index maps fresh memory again),
  * "sort" (1 hand-written radix sort [default], 0 cub), "host_chunks" (pipeline chunks of the
  * host-buffer API, default 8), "queue_cap" (tests: per-sample traversal queue entries, at most
  * the compiled 12), "verbose", "smem_pad" (diagnosis). */

@@ -100,6 +100,15 @@ int64_t pto_reference_face_loop(const pto_kdtree *t, const pto_point *vertices,
 
 int pto_max_threads(void);
 
+/* Per-face transfer + texture output (pt_texture_oracle.c): src/pointsTransfer.cpp:465-611 and
+ * draw_triangle :66-107.  idx[n_vertices * k]: neighbour lists of the mesh vertices; bgra:
+ * res * res * 4 bytes (B G R A), zeroed by the caller; stats[2] (may be NULL) += sub-triangles
+ * drawn, inside points.  Sequential: later faces overwrite earlier ones, as in the reference. */
+int pto_texture_faces(const pto_point *pts, const pto_point *vertices, const int32_t *idx, int k,
+                      const int32_t *faces, int64_t n_faces, int res, uint8_t *bgra, int64_t *stats);
+/* 25x25 dilate + gutter (src/pointsTransfer.cpp:593-611); in / out: res * res * 4 bytes */
+int pto_texture_pad(const uint8_t *in, int res, uint8_t *out);
+
 /* Host restatement of the synthetic workload generators (pt_synth_host.c): the clouds and mesh
  * samples of BASELINE.json's configs on the host cores, without any CUDA code (bench.py's
  * reference arm).  kind: 0 heightfield scan, 1 skewed clusters.  Returns 0. */

@@ -27,7 +27,7 @@ def build(force=False):
     """Compile the C restatement (gcc, oracle/Makefile)."""
     if force or not os.path.exists(_LIB_PATH) or (
         os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f))
-                                          for f in ("pt_oracle.c", "pt_synth_host.c", "pt_oracle.h"))
+                                          for f in ("pt_oracle.c", "pt_synth_host.c", "pt_texture_oracle.c", "pt_oracle.h"))
     ):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
                        stdout=subprocess.DEVNULL)
@@ -103,6 +103,10 @@ def lib():
         L.pto_synth_cloud.argtypes = [vp, i64, i32, u64, u64, dbl, dbl, dbl, dbl, dbl, i32]
         L.pto_synth_samples.restype = i32
         L.pto_synth_samples.argtypes = [vp, i64, i64, dbl, dbl, dbl, dbl, i32]
+        L.pto_texture_faces.restype = i32
+        L.pto_texture_faces.argtypes = [vp, vp, vp, i32, vp, i64, i32, vp, vp]
+        L.pto_texture_pad.restype = i32
+        L.pto_texture_pad.argtypes = [vp, i32, vp]
         _lib = L
     return _lib
 
@@ -227,4 +231,29 @@ def synth_samples(gu, gv, u0=0.0, u1=1000.0, v0=0.0, v1=1000.0, center=False):
     out = np.empty(int(gu) * int(gv), dtype=POINT_DTYPE)
     rc = lib().pto_synth_samples(_ptr(out), int(gu), int(gv), u0, u1, v0, v1, 1 if center else 0)
     assert rc == 0, rc
+    return out
+
+
+def texture(points, vertices, idx, faces, resolution, pad=True):
+    """The reference's face loop + texture post-process (pt_texture_oracle.c).  idx: int32
+    [n_vertices, k] neighbour lists.  Returns (bgra uint8 [res,res,4], (triangles, inside))."""
+    points, vertices = _chk_points(points), _chk_points(vertices)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
+    img = np.zeros((resolution, resolution, 4), dtype=np.uint8)
+    stats = np.zeros(2, dtype=np.int64)
+    rc = lib().pto_texture_faces(_ptr(points), _ptr(vertices), _ptr(idx), idx.shape[1], _ptr(faces),
+                                 faces.shape[0], resolution, _ptr(img), _ptr(stats))
+    assert rc == 0, rc
+    if pad:
+        out = np.empty_like(img)
+        assert lib().pto_texture_pad(_ptr(img), resolution, _ptr(out)) == 0
+        img = out
+    return img, (int(stats[0]), int(stats[1]))
+
+
+def texture_pad(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.empty_like(img)
+    assert lib().pto_texture_pad(_ptr(img), img.shape[0], _ptr(out)) == 0
     return out

@@ -53,7 +53,14 @@ def test_no_gpu_fails_loudly(cli, pkg, tmp_path):
     r = subprocess.run([cli, str(tmp_path / "c.ply"), str(tmp_path / "m.ply")],
                        capture_output=True, text=True, cwd=tmp_path)
     assert "PC Point count: 50" in r.stdout
-    assert "no CUDA device" in r.stderr and not (tmp_path / "transferred.ply").exists()
+    assert "no CUDA device" in r.stderr and not (tmp_path / "texture.png").exists()
+
+
+def test_bad_k_is_a_message_not_a_crash(cli, tmp_path):
+    # every error path of the reference prints and returns 0 (:116-120, :137-141)
+    for k in ("-3", "0", "99"):
+        r = subprocess.run([cli, "-k", k, "a.ply", "b.ply"], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 0 and "-k must be" in r.stderr
 
 
 @pytest.mark.gpu
@@ -65,8 +72,10 @@ def test_cli_end_to_end(cli, pkg, pto, tmp_path):
     V = pkg.synth.samples_host(12, side=20.0)
     F = pkg.synth.grid_faces(12, 12)
     write_cloud(tmp_path / "c.ply", P)
+    V["U"] = V["ver"][:, 0] / 20.0 * 0.9 + 0.05
+    V["V"] = V["ver"][:, 1] / 20.0 * 0.9 + 0.05
     write_mesh(tmp_path / "m.ply", V, F)
-    r = subprocess.run([cli, str(tmp_path / "c.ply"), str(tmp_path / "m.ply")],
+    r = subprocess.run([cli, "-R", "512", "-p", "transferred.ply", str(tmp_path / "c.ply"), str(tmp_path / "m.ply")],
                        capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0, r.stderr
     for label in ("PC Point count: 20000", "Read point set in:", "Built Kd tree in:",
@@ -74,12 +83,22 @@ def test_cli_end_to_end(cli, pkg, pto, tmp_path):
                   "Neighbor search total time:", "Draw triangles total time:", "Output time:",
                   "Total real time:", "VIRT:", "RES:"):
         assert label in r.stdout, label
+    # the reference's artefact: texture.png in the working directory (:613), equal to the oracle's
+    # restatement of the face loop + post-process on the same inputs (K = 20, :128)
+    import cv2
+    png = cv2.imread(str(tmp_path / "texture.png"), cv2.IMREAD_UNCHANGED)       # BGRA, as cv::Mat
+    assert png is not None and png.shape == (512, 512, 4)
+    Vm = V.copy()
+    Vm["color"] = np.array([10, 20, 30])                  # what write_mesh put in the file
+    idx, d2 = pto.knn_bruteforce(P, Vm, 20)
+    ref_img, (ntri, nin) = pto.texture(P, Vm, idx, F, 512, pad=True)
+    assert ntri > len(F) and nin > 0
+    assert np.array_equal(png, ref_img)
     rows = [l.split() for l in open(tmp_path / "transferred.ply").read().split("end_header\n")[1].splitlines()]
     verts = np.array(rows[:144], dtype=np.float64)
     faces = np.array(rows[144:], dtype=np.int64)
     assert np.array_equal(faces[:, 1:], F)
-    # same K = 20 as the reference (:128); %.17g text round-trips the fp64 values exactly
-    idx, d2 = pto.knn_bruteforce(P, V, 20)
+    # %.17g text round-trips the fp64 values exactly
     rgba, nrm = pto.blend(P, idx, d2)
     assert np.array_equal(verts[:, 8:11].astype(np.uint8), rgba[:, :3])
     assert np.allclose(verts[:, 3:6], nrm, rtol=1e-5, atol=1e-7)
