@@ -470,7 +470,12 @@ def main():
             # exchanged ONCE here, so the owner step needs no collective
             boxes = pkg.dist.gather_boxes(own_box)
             pos, attrs, ids = pkg.dist.exchange_ghosts(pos, attrs, ids, boxes, halo)
-    pkg.DeviceTree(pos, attrs, ids).close()     # warm-up build (module load, allocator)
+    # the timed build is a REBUILD: the first build maps the library's private memory pool, which
+    # is kept (pool_keep_mb) so that the second one measures the kernels, not cuMemMap
+    pkg.set_option("pool_keep_mb", 98304)
+    t0 = time.perf_counter()
+    pkg.DeviceTree(pos, attrs, ids).close()     # first build (module load, pool mapping)
+    first_build_wall_ms = (time.perf_counter() - t0) * 1e3
     t0 = time.perf_counter()
     tree = pkg.DeviceTree(pos, attrs, ids)
     build_wall_ms = (time.perf_counter() - t0) * 1e3
@@ -620,7 +625,8 @@ def main():
                      "peak_source": peak_src, "per": "GPU",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel": kernel,
                      "kernel_ms": ms_per_step},
-        "build": {"ms": info.build_ms, "wall_ms": build_wall_ms,
+        "build": {"ms": info.build_ms, "wall_ms": build_wall_ms, "first_build_wall_ms": first_build_wall_ms,
+                  "note": "rebuild with the library's memory pool already mapped (pool_keep_mb)",
                   "points_per_s": int(info.n_points) / (info.build_ms * 1e-3),
                   "roofline_frac": build_achieved / peak, "achieved_gbs": build_achieved,
                   "leaves": int(info.n_leaves), "index_bytes": int(info.device_bytes)},
