@@ -99,4 +99,6 @@ class ShardedTransfer:
         s = dict(self.slab.stats)
         s["routed_to_other_slabs"] = away
         s["crossing"] = self.slab.crossing_count() if s.get("path") == "fast" else s.get("crossing", 0)
+        if s.get("path") == "fast":
+            s["halo_rows_per_peer"] = [int(v) for v in self.slab._last_counts.tolist()]
         return s

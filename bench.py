@@ -308,7 +308,7 @@ def run_reference_arm(args, pkg, world, rank):
 
 # ---------------------------------------------------------------------------------------------
 def verify_by_ball(pkg, pto, torch, dist, world, rank, dev, own_pos, own_attrs, first_id, q, res, k,
-                   radius, n_check):
+                   radius, n_check, cuts=None):
     """Exact check of sampled results against the oracle by restriction: every true neighbour of
     a sample lies within its reported k-th distance (or the radius bound), so the oracle's brute
     force over the points of ALL slabs inside that ball must reproduce ids, colours and normals.
@@ -317,6 +317,13 @@ def verify_by_ball(pkg, pto, torch, dist, world, rank, dev, own_pos, own_attrs, 
     import numpy as np
     m = q.shape[0]
     sel = torch.linspace(0, m - 1, min(n_check, m), device=dev).long()
+    if cuts is not None and m:
+        # half of the checked samples are the ones closest to a slab boundary: the samples whose
+        # neighbours really come from two ranks (ghost zone / halo exchange + merge)
+        inner = torch.tensor([c for c in cuts if math.isfinite(c)], dtype=torch.float64, device=dev)
+        gap = (q[:, :1] - inner[None, :]).abs().min(dim=1).values
+        near = torch.topk(gap, min(n_check // 2, m), largest=False).indices
+        sel = torch.cat([sel[: sel.numel() - near.numel()], near])       # same count on every rank
     d_idx = res["idx"][sel]
     pos_k = None
     # k-th distance of each checked sample: recompute from the last valid neighbour -- its
@@ -549,7 +556,8 @@ def main():
         res["d2"] = d2
         torch.cuda.synchronize()
         verified = verify_by_ball(pkg, pto, torch, dist, world, rank, dev, own_pos, own_attrs, first, q, res,
-                                  k, w.radius, 48 if world == 1 else 24)
+                                  k, w.radius, 48 if world == 1 else 24,
+                                  cuts=None if st is None else cuts)
 
     # ---- e2e with pinned host buffers ------------------------------------------------------------
     out_idx = torch.empty((m, k), dtype=torch.int32, pin_memory=True)

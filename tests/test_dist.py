@@ -209,3 +209,20 @@ def test_box_lower_bound_is_conservative(pkg):
     p = torch.from_numpy(rng.random((1000, 3))) * hi          # points inside the box
     d2 = ((q - p) ** 2).sum(1)
     assert bool((lb <= d2).all())
+
+
+def test_halo_without_own_box_is_rejected():
+    """A ghost-augmented index's bbox already contains the ghost points: the ghost-zone test must
+    be given the box of the slab's OWN points, never silently the inflated one."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    pkg = ge.package()
+
+    class Eng:
+        device = torch.device("cpu")
+        n_points = 1
+        bbox_lo = torch.zeros(3, dtype=torch.float64)
+        bbox_hi = torch.ones(3, dtype=torch.float64)
+
+    with pytest.raises(ValueError):
+        pkg.dist.SlabTransfer(Eng(), halo=1.0)
