@@ -61,7 +61,7 @@ int set_option(const char *name, int value)
 {
     if (!name) return PT_ERR_INVALID_ARG;
     if (!strcmp(name, "knn_variant")) {
-        if (value != -1 && value != 0 && value != 2 && value != 5 && value != 6 && value != 7) return PT_ERR_INVALID_ARG;
+        if (value != -1 && value != 0 && value != 2 && value != 5 && value != 6) return PT_ERR_INVALID_ARG;
         g_knn_variant.store(value);
         return PT_OK;
     }

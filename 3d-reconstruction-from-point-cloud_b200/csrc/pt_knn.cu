@@ -363,9 +363,8 @@ __global__ void __launch_bounds__(256) empty_result_kernel(const QueryParams P)
 }  // namespace pt
 #include "pt_knn_traverse.cuh"
 #include "pt_knn_thread.cuh"
-#include "pt_knn_grid.cuh"
-#include "pt_knn_gridwalk.cuh"
 #include "pt_knn_scan.cuh"
+#include "pt_knn_grid.cuh"
 namespace pt {
 
 // Launch plan.  Every launch gets its OWN hand-over workspace (two sample lists with their
@@ -386,10 +385,9 @@ static int launch_chain(pt_index *ix, const QueryParams &qp, int variant, cudaSt
     cudaError_t e = cudaMemsetAsync(ws, 0, 8 * sizeof(uint32_t), s);     // both counters at once
     if (e != cudaSuccess) rc = map_cuda_error(e);
     QueryParams q2 = qp;
-    const bool grid_first = variant == 6 || variant == 7;
-    if (rc == PT_OK && (variant == 6 || variant == 7)) {
-        rc = variant == 6 ? launch_grid<PT>(qp, ix->sm_count, count1, list1, s)
-                          : launch_scan<PT, true>(qp, count1, list1, s);
+    const bool grid_first = variant == 6;
+    if (rc == PT_OK && variant == 6) {
+        rc = launch_grid<PT>(qp, ix->sm_count, count1, list1, s);
         // A short hand-over list is answered by the warp kernel (one warp per sample: a few
         // samples cost ~30 us there, but a whole ~110 us block latency in the scan / thread
         // kernels); a long one by the scan / thread kernel in list mode (min_count).
@@ -433,7 +431,7 @@ int launch_query(pt_index *ix, const QueryParams &qp_in, cudaStream_t s)
     }
     int variant = opt_knn_variant();
     const bool bounded = qp.r2_per_query != nullptr || qp.r2 < INFINITY;
-    const bool have_grid = (variant < 0 || variant == 6 || variant == 7) && grid_plan(ix, qp.k, qp.r2, qp.grid) > 0;
+    const bool have_grid = (variant < 0 || variant == 6) && grid_plan(ix, qp.k, qp.r2, qp.grid) > 0;
     if (!have_grid) qp.grid.n_attempts = 0;
     if (have_grid && verbose()) {
         fprintf(stderr, "[points_transfer] grid plan k=%d:", qp.k);
@@ -444,7 +442,7 @@ int launch_query(pt_index *ix, const QueryParams &qp_in, cudaStream_t s)
         }
         fprintf(stderr, "\n");
     }
-    if ((variant == 6 || variant == 7) && !have_grid) variant = -1;
+    if (variant == 6 && !have_grid) variant = -1;
     if (variant < 0) {
         // auto (measured): the grid kernel first whenever the index has
         // cell tables.  Without them (tiny clouds, kd-refined order):

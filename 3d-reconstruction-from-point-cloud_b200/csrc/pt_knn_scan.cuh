@@ -26,9 +26,7 @@ constexpr uint32_t SCAN_SM = (1u << SCAN_SB) - 1u;
 #ifndef PT_SCAN_MIN_BLOCKS
 #define PT_SCAN_MIN_BLOCKS 20
 #endif
-// GRID = false: candidates come from the best-first walk of the box pyramid (variant 5);
-// GRID = true : from the cell runs of the uniform grid (variant 7, pt_knn_gridwalk.cuh).
-template <typename PT, bool GRID>
+template <typename PT>
 __global__ void __launch_bounds__(T_THREADS, PT_SCAN_MIN_BLOCKS)
 knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
 {
@@ -53,7 +51,7 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     const uint32_t qi = blockIdx.x * T_THREADS + tid;
     const bool live = qi < m_eff;
     const uint32_t q = live ? (P.qlist ? P.qlist[qi] : qi) : 0u;
-    bool done = !live || (GRID ? P.grid.n_attempts == 0 : P.t_levels == 0);
+    bool done = !live || P.t_levels == 0;
     bool overflow = false;
 
     double qx = 0, qy = 0, qz = 0, r2 = 0;
@@ -69,9 +67,7 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     int hn = 0;                      // slots in use
     uint32_t rtk = 0xffffffffu;      // truncated key (key >> 5) of the current k-th candidate ...
     int rslot = 0;                   // ... and its slot -- meaningful once hn == k
-    Traverser<PT, T_THREADS> tr(P, pqk, pqw, qx, qy, qz, !done && !GRID);
-    GridWalker<PT> gw(P, qx, qy, qz, !done && GRID);
-    if (GRID && live && P.grid.n_attempts == 0) gw.failed = true;      // no tables: hand over
+    Traverser<PT, T_THREADS> tr(P, pqk, pqw, qx, qy, qz, !done);
 
     // exact (d2, index) of an entry, re-read from the sorted cloud (rare: only on equal keys)
     auto exact_of = [&](uint32_t pos, double &d, int &idx) {
@@ -110,36 +106,24 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     };
 
     for (;;) {
-        // ---- the next run of points of every lane: a 32-point leaf or a cell run -------------------
-        uint32_t rb = 0, re = 0;
-        if (GRID) {
-            gw.next_run(bound, hn < k, done, rb, re);
-            if (gw.take_restart()) {       // a larger block is searched from an empty list
-                hn = 0;
-                rtk = 0xffffffffu;
-                bound = bound_r;
-                for (int g = 0; g < KG; ++g) kq[g * T_THREADS] = make_uint4(0u, 0u, 0u, 0u);
-            }
-        } else {
-            const int leaf = tr.next_leaf(bound, hn < k, done);
-            if (leaf >= 0) { rb = (uint32_t)leaf * LEAF; re = rb + LEAF; }
-        }
+        const int leaf = tr.next_leaf(bound, hn < k, done);
         if (__all_sync(0xffffffffu, done)) break;
 
-        // ---- scan phase: every lane that holds a run scans it, 8 points per chunk ----------------
+        // ---- leaf phase: every lane that holds a leaf scans it, 8 points per chunk -------------
+        const uint32_t base = (uint32_t)(leaf < 0 ? 0 : leaf) * LEAF;
 #pragma unroll 1
-        for (; __any_sync(0xffffffffu, rb < re); rb += PT_T_CHUNK) {
+        for (int chunk = 0; chunk < LEAF / PT_T_CHUNK; ++chunk) {
             int pend = 0;
-            if (rb < re) {
+            if (leaf >= 0) {
 #pragma unroll
                 for (int p = 0; p < PT_T_CHUNK; ++p) {
-                    const uint32_t pi = rb + p;
+                    const uint32_t pi = base + chunk * PT_T_CHUNK + p;
                     double px, py, pz;
                     int pidx;
-                    PointLoad<PT>::load(P.pts, min(pi, re - 1), px, py, pz, pidx);
+                    PointLoad<PT>::load(P.pts, pi, px, py, pz, pidx);
                     const double d = dist2_exact(qx, qy, qz, px, py, pz);
                     const uint32_t cf = __float_as_uint(__double2float_rd(d));
-                    if (pi < re && pi < P.n && d <= r2 && (hn < k || (cf >> SCAN_SB) <= rtk)) {
+                    if (pi < P.n && d <= r2 && (hn < k || (cf >> SCAN_SB) <= rtk)) {
                         pe[pend * T_THREADS] = ((unsigned long long)cf << 32) | pi;
                         ++pend;
                     }
@@ -175,11 +159,11 @@ knn_scan_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
             bound = fminf(__uint_as_float((rtk + 1u) << SCAN_SB), bound_r);
             // the siblings queued during the first dive were pushed with an infinite bound:
             // most of them are dead now, which keeps a small queue sufficient
-            if (!GRID && first && bound < bound_r) tr.compact(bound);
+            if (first && bound < bound_r) tr.compact(bound);
         }
     }
 
-    overflow = GRID ? gw.failed : tr.proof_failed(bound);
+    overflow = tr.proof_failed(bound);
 #ifdef PT_STATS
     {
         unsigned v = (live && overflow) ? 1u : 0u, w = live ? 1u : 0u;
@@ -232,15 +216,15 @@ static inline size_t scan_kernel_smem(int k)
     return (size_t)T_THREADS * (kp * 8 + (size_t)TPD_CAP * 8 + (size_t)TPQ_CAP * 8);
 }
 
-template <typename PT, bool GRID = false>
+template <typename PT>
 static int launch_scan(const QueryParams &qp, uint32_t *count, uint32_t *list, cudaStream_t s)
 {
     const size_t smem = scan_kernel_smem(qp.k) + (size_t)opt_smem_pad();
     if (smem > 48 * 1024)   // only the occupancy probe (smem_pad) ever exceeds the default limit
-        PT_CUDA(cudaFuncSetAttribute(knn_scan_kernel<PT, GRID>,
+        PT_CUDA(cudaFuncSetAttribute(knn_scan_kernel<PT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned blocks = (qp.m + T_THREADS - 1) / T_THREADS;
-    knn_scan_kernel<PT, GRID><<<blocks, T_THREADS, smem, s>>>(qp, count, list);
+    knn_scan_kernel<PT><<<blocks, T_THREADS, smem, s>>>(qp, count, list);
     count_launch();
     PT_CUDA(cudaGetLastError());
     return PT_OK;

@@ -453,10 +453,15 @@ def main():
     L = pkg.synth.L_DOMAIN
     M = gu * gv
     # ---- this rank's slab of the cloud (x-range [u0, u1), global ids first .. first + n) ------
-    per = n_total // world
-    first = rank * per
-    n = per if rank < world - 1 else n_total - first
-    u0, u1 = rank * L / world, (rank + 1) * L / world
+    # Inner cuts sit 0.45 sample spacings off the regular L*r/N positions: with regular cuts no
+    # k-NN ball of the mesh grids of cfg3 / cfg4 reaches a cut (the nearest sample column is half
+    # a spacing away) and the ghost zones / the halo exchange would never carry a neighbour.
+    cut_at = [0.0] + [r * L / world + 0.45 * L / gu for r in range(1, world)] + [L]
+    counts_per_slab = [int(round(n_total * (cut_at[r + 1] - cut_at[r]) / L)) for r in range(world)]
+    counts_per_slab[-1] = n_total - sum(counts_per_slab[:-1])
+    first = sum(counts_per_slab[:rank])
+    n = counts_per_slab[rank]
+    u0, u1 = cut_at[rank], cut_at[rank + 1]
     pos, attrs = pkg.synth.cloud_device(n, w.seed, u0=u0, u1=u1, kind=w.kind, sigma=w.sigma,
                                         first_index=first, device=dev)
     own_pos, own_attrs = pos, attrs
@@ -508,7 +513,7 @@ def main():
 
     st = None
     if world > 1:
-        cuts = [-math.inf] + [r * L / world for r in range(1, world)] + [math.inf]
+        cuts = [-math.inf] + cut_at[1:-1] + [math.inf]
         st = pkg.sharded.ShardedTransfer(pkg.dist.CudaSlabEngine(tree), cuts, k, (M + world - 1) // world,
                                          own_box=own_box, halo=halo)
 

@@ -41,7 +41,7 @@ def _default_options(pkg):
 
 # (knn_variant, order): grid / thread / warp / scan kernel x Morton, Hilbert, Hilbert + kd
 # refinement (order 2 has no cell tables: variant 6 then falls through to the auto rule)
-MODES = [(7, 1), (7, 0), (6, 1), (6, 0), (-1, 1), (2, 1), (0, 1), (5, 1), (2, 0), (2, 2), (0, 2), (5, 2), (5, 0), (6, 2)]
+MODES = [(6, 1), (6, 0), (-1, 1), (2, 1), (0, 1), (5, 1), (2, 0), (2, 2), (0, 2), (5, 2), (5, 0), (6, 2)]
 
 
 @pytest.mark.parametrize("mode", MODES, ids=lambda m: f"variant{m[0]}-order{m[1]}")
@@ -87,7 +87,7 @@ def test_f64_storage_forced_and_f32_rejected(pkg, pto, torch_cuda):
         assert np.array_equal(idx, ref_idx) and np.array_equal(d2, ref_d2)
 
 
-@pytest.mark.parametrize("variant", [7, 6, 5, 2, 0])
+@pytest.mark.parametrize("variant", [6, 5, 2, 0])
 @pytest.mark.parametrize("k", [1, 8, 16, 20, 32])
 def test_surface_cloud_vs_kdtree_oracle(k, variant, pkg, pto, torch_cuda):
     pkg.set_option("knn_variant", variant)
@@ -112,7 +112,7 @@ def test_gpu_d2_is_the_reference_metric(pkg, pto, torch_cuda):
         pytest.skip("oracle/_ref was never built (/root/reference absent at build time)")
     P = pkg.synth.cloud_host(100_000, seed=3, side=50.0)
     V = pkg.synth.samples_host(40, side=50.0)
-    for variant in (7, 6, 5, 2, 0):
+    for variant in (6, 5, 2, 0):
         pkg.set_option("knn_variant", variant)
         with pkg.Tree(P) as tree:
             idx, d2 = tree.knn(V, 16)
@@ -142,7 +142,7 @@ def test_reference_call_site_shape(pkg, pto, torch_cuda):
                 assert [g[1] for g in got] == ref_d2[v].tolist()
 
 
-@pytest.mark.parametrize("variant", [7, 6, 5, 2])
+@pytest.mark.parametrize("variant", [6, 5, 2])
 def test_device_api_ids_and_radius_per_query(variant, pkg, pto, torch_cuda):
     pkg.set_option("knn_variant", variant)
     torch = torch_cuda
@@ -183,7 +183,7 @@ def test_device_api_ids_and_radius_per_query(variant, pkg, pto, torch_cuda):
     tree.close()
 
 
-@pytest.mark.parametrize("variant", [7, 6, 5, 2])
+@pytest.mark.parametrize("variant", [6, 5, 2])
 @pytest.mark.parametrize("n_slabs,k", [(2, 8), (3, 16), (8, 32)])
 def test_slab_merge_equals_single_index(n_slabs, k, variant, pkg, pto, torch_cuda):
     pkg.set_option("knn_variant", variant)
@@ -279,7 +279,7 @@ def test_tiny_queue_stays_exact(cap, variant, pkg, pto, golden_dir, torch_cuda):
                 assert np.array_equal(d2, z[f"d2_k{k}"]), (name, k)
 
 
-@pytest.mark.parametrize("variant", [-1, 7, 6, 5, 2, 0])
+@pytest.mark.parametrize("variant", [-1, 6, 5, 2, 0])
 def test_edge_cases(variant, pkg, torch_cuda):
     pkg.set_option("knn_variant", variant)
     empty = np.zeros(0, dtype=pkg.POINT_DTYPE)
@@ -376,7 +376,7 @@ def test_baseline_config_shapes_vs_oracle(cfg, n, g, k, pkg, pto, torch_cuda):
     Q = pkg.synth.queries_to_host(q)
     ref_idx, ref_d2 = pto.KdTree(P).knn(Q, k, radius=-1.0 if radius is None else radius)
     ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
-    for variant in (7, 6, 5, 2, 0):
+    for variant in (6, 5, 2, 0):
         pkg.set_option("knn_variant", variant)
         tree = pkg.DeviceTree(pos, attrs)
         m = q.shape[0]

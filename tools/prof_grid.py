@@ -39,9 +39,9 @@ def timed(tree, outs, want_d2, reps=7):
 
 results = {}
 MODES = (("thread/order2", 2, 2, 1), ("scan/order2", 2, 5, 1), ("thread/order1", 1, 2, 1),
-         ("grid/tma", 1, 6, 1), ("grid/ldgsts", 1, 6, 0), ("gridwalk", 1, 7, 1))
+         ("grid/tma", 1, 6, 1), ("grid/ldgsts", 1, 6, 0))
 if os.environ.get("PROF_GRID_SHORT"):
-    MODES = (MODES[0], MODES[3], MODES[5])
+    MODES = (MODES[0], MODES[3], MODES[4])
 for name, order, variant, tma in MODES:
     pkg.set_option("order", order)
     pkg.set_option("knn_variant", variant)
