@@ -17,7 +17,6 @@ static std::atomic<int> g_sort{1};    // 1 hand-written radix sort (default), 0 
 static std::atomic<int> g_order{1};   // 0 Morton, 1 Hilbert (default), 2 Hilbert + kd refinement (no cell tables)
 static std::atomic<int> g_grid{1};        // build the uniform-grid cell tables (pt_grid.cu)
 static std::atomic<int> g_grid_tma{1};    // stage candidate runs with cp.async.bulk (0: per-lane cp.async)
-static std::atomic<int> g_host_stream{1};        // host-buffer calls: one streamed launch for large batches
 static std::atomic<int> g_pool_keep_mb{2048};   // temporaries kept cached in the library's pool after a build / free
 static std::atomic<int> g_sort_bits{48};  // ordered key bits, from the top (cells contiguous down to level 16)
 
@@ -51,7 +50,6 @@ int opt_grid() { return g_grid.load(); }
 int opt_grid_tma() { return g_grid_tma.load(); }
 int opt_sort_bits() { return g_sort_bits.load(); }
 size_t opt_pool_keep_bytes() { return (size_t)g_pool_keep_mb.load() << 20; }
-int opt_host_stream() { return g_host_stream.load(); }
 static std::atomic<int> g_host_chunks{8};   // host-buffer API: pipeline chunks per call (one stream each, up to 16)
 int opt_host_chunks() { return g_host_chunks.load(); }
 static std::atomic<int> g_queue_cap{1 << 20};   // tests: shrink the per-sample queue (exactness under spilling)
@@ -73,7 +71,6 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "grid_tma")) { g_grid_tma.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { g_sort_bits.store(value); return PT_OK; }
     if (!strcmp(name, "pool_keep_mb")) { g_pool_keep_mb.store(value < 0 ? 0 : value); return PT_OK; }
-    if (!strcmp(name, "host_stream")) { g_host_stream.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { g_queue_cap.store(value < 2 ? 2 : value); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { g_host_chunks.store(value < 1 ? 1 : (value > 64 ? 64 : value)); return PT_OK; }
@@ -90,7 +87,6 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "grid_tma")) { *value = g_grid_tma.load(); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { *value = g_sort_bits.load(); return PT_OK; }
     if (!strcmp(name, "pool_keep_mb")) { *value = g_pool_keep_mb.load(); return PT_OK; }
-    if (!strcmp(name, "host_stream")) { *value = g_host_stream.load(); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { *value = g_smem_pad.load(); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { *value = g_queue_cap.load(); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { *value = g_host_chunks.load(); return PT_OK; }
@@ -153,7 +149,7 @@ static void destroy_index(pt_index *ix)
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" (default 2 GiB) stays cached for the next build
     cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->fallback_word); cudaFree(ix->inv_perm);
-    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out); cudaFree(ix->ws_flags);
+    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out);
     for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
     for (auto &e : ix->cev) if (e) cudaEventDestroy(e);
     for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);
@@ -332,7 +328,6 @@ static int query_device_on(pt_index *ix, const double *queries_xyz, size_t m, in
     QueryParams qp{};
     fill_params(ix, qp);
     qp.queries = queries_xyz;
-    qp.q_stride = 3;
     qp.r2_per_query = radius2_per_query;
     qp.m = (uint32_t)m;
     qp.k = k;
@@ -426,11 +421,6 @@ int pt_halo_merge_device(pt_cand *own_cand, const pt_cand *back, const int32_t *
 // the H2D copy of the 80-byte records, the kernels and the D2H copy of the results overlap
 // (pinned caller buffers make the copies truly asynchronous; pageable ones still work).
 // Ghost-zone check of a slab index (pt_transfer_slab): host copies of the slabs' boxes.
-static int host_query_streamed(pt_index *ix, const void *queries, size_t m, int k, double radius,
-                               int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out,
-                               bool queries_are_xyz);
-static bool stream_memops();
-
 struct GhostCheck {
     const double *boxes;   // n_ranks x 6, host
     int n_ranks, self;
@@ -448,10 +438,6 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
     if (ghost && ghost->needs_exchange) *ghost->needs_exchange = 0;
     if (m == 0) return PT_OK;
     PT_CUDA(cudaSetDevice(ix->device));
-    // large plain calls on an index with cell tables: one streamed launch (see below)
-    if (!ghost && m >= 65536 && opt_host_stream() && ix->grid.n_tables > 0 &&
-        (opt_knn_variant() < 0 || opt_knn_variant() == 6) && stream_memops())
-        return host_query_streamed(ix, queries, m, k, radius, idx_out, d2_out, rgba_out, normal_out, queries_are_xyz);
     cudaStream_t s = ix->stream;
     const size_t mk = m * (size_t)k;
     const bool need_d2 = d2_out || ghost;      // the ghost check reads the k-th d2 on the device
@@ -538,133 +524,6 @@ static int host_query(pt_index *ix, const void *queries, size_t m, int k, double
     PT_CUDA(cudaStreamSynchronize(s));
     if (ghost && ghost->needs_exchange) *ghost->needs_exchange = flag ? 1 : 0;
     ix->last_h2d_ms = 0.f;          // overlapped with the kernels: only the total is meaningful
-    ix->last_d2h_ms = 0.f;
-    cudaEventElapsedTime(&ix->last_query_ms, ix->ev[0], ix->ev[3]);
-    return PT_OK;
-}
-
-// ---- streamed host-buffer call ------------------------------------------------------------------
-// One launch of the kernel chain over ALL samples instead of one per pipeline chunk (a 25 k-sample
-// launch of the grid kernel costs ~85 us where its share of a full launch is ~48 us): the H2D
-// copies of the chunks are issued first, each followed in stream order by a 32-bit write of the
-// call's epoch to in_flag[chunk] (stream memory operation); the grid kernel, which answers the
-// samples in index order, waits for a chunk's flag before it reads the chunk; when the last
-// sample of a chunk has been answered the kernel writes out_flag[chunk], on which the D2H copies
-// of that chunk wait (stream wait-value).  Samples handed to the second-stage kernels complete
-// their chunks at the end of the chain (stream_finish_kernel).
-typedef int (*StreamMemOp)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned int, unsigned int);
-static StreamMemOp g_wait32 = nullptr, g_write32 = nullptr;
-static std::atomic<int> g_memops{-1};    // -1 unknown, 0 unavailable, 1 resolved
-
-static bool stream_memops()
-{
-    int st = g_memops.load();
-    if (st < 0) {
-        void *w = nullptr, *r = nullptr;
-        cudaDriverEntryPointQueryResult q1, q2;
-        const bool ok = cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q1) == cudaSuccess &&
-                        cudaGetDriverEntryPoint("cuStreamWriteValue32", &r, cudaEnableDefault, &q2) == cudaSuccess &&
-                        q1 == cudaDriverEntryPointSuccess && q2 == cudaDriverEntryPointSuccess && w && r;
-        cudaGetLastError();
-        if (ok) { g_wait32 = (StreamMemOp)w; g_write32 = (StreamMemOp)r; }
-        st = ok ? 1 : 0;
-        g_memops.store(st);
-    }
-    return st == 1;
-}
-
-static int host_query_streamed(pt_index *ix, const void *queries, size_t m, int k, double radius,
-                               int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out,
-                               bool queries_are_xyz)
-{
-    cudaStream_t s = ix->stream;
-    const size_t mk = m * (size_t)k;
-    size_t off_d2 = 0, off_idx = off_d2 + (d2_out ? mk * 8 : 0);
-    size_t off_nrm = off_idx + (idx_out ? mk * 4 : 0);
-    size_t off_rgba = off_nrm + (normal_out ? m * 12 : 0);
-    size_t total = off_rgba + (rgba_out ? m * 4 : 0);
-    const size_t rec = queries_are_xyz ? 24 : PT_POINT_STRIDE;
-    PT_TRY(grow(&ix->ws_raw, &ix->ws_raw_bytes, m * rec));
-    PT_TRY(grow(&ix->ws_out, &ix->ws_out_bytes, total + 16));
-    size_t want = (size_t)opt_host_chunks();
-    if (want < 2) want = 2;
-    const size_t chunk = (((m + want - 1) / want) + 31) & ~(size_t)31;
-    const uint32_t n_chunks = (uint32_t)((m + chunk - 1) / chunk);
-    const size_t flag_words = 3 * (size_t)n_chunks + 4;
-    if (flag_words * 4 > ix->ws_flags_bytes) {
-        if (ix->ws_flags) cudaFree(ix->ws_flags);
-        ix->ws_flags = nullptr; ix->ws_flags_bytes = 0;
-        PT_CUDA(cudaMalloc(&ix->ws_flags, flag_words * 4 * 2));
-        PT_CUDA(cudaMemset(ix->ws_flags, 0, flag_words * 4 * 2));
-        ix->ws_flags_bytes = flag_words * 4 * 2;
-        ix->stream_epoch = 0;
-    }
-    const uint32_t epoch = ++ix->stream_epoch;
-    uint32_t *in_flag = ix->ws_flags, *out_flag = in_flag + n_chunks, *done = out_flag + n_chunks, *err = done + n_chunks;
-    for (int i = 0; i < 2; ++i) {
-        if (!ix->cs[i]) PT_CUDA(cudaStreamCreateWithFlags(&ix->cs[i], cudaStreamNonBlocking));
-        if (!ix->cev[i]) PT_CUDA(cudaEventCreateWithFlags(&ix->cev[i], cudaEventDisableTiming));
-    }
-    cudaStream_t s_in = ix->cs[0], s_out = ix->cs[1];
-    char *o = (char *)ix->ws_out;
-    uint32_t h_err = 0;
-    auto issue = [&]() -> int {
-        PT_CUDA(cudaEventRecord(ix->ev[0], s));
-        PT_CUDA(cudaStreamWaitEvent(s_in, ix->ev[0], 0));
-        PT_CUDA(cudaStreamWaitEvent(s_out, ix->ev[0], 0));
-        // 1. the samples, chunk by chunk, each followed by its flag
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            const size_t c0 = (size_t)c * chunk, cm = m - c0 < chunk ? m - c0 : chunk;
-            PT_CUDA(cudaMemcpyAsync((char *)ix->ws_raw + c0 * rec, (const char *)queries + c0 * rec, cm * rec,
-                                    cudaMemcpyHostToDevice, s_in));
-            if (g_write32(s_in, (unsigned long long)(uintptr_t)(in_flag + c), epoch, 0) != 0) return PT_ERR_CUDA;
-        }
-        // 2. ONE kernel chain over all samples
-        PT_CUDA(cudaMemsetAsync(done, 0, sizeof(uint32_t) * (n_chunks + 1), s));     // counts + error word
-        QueryParams qp{};
-        fill_params(ix, qp);
-        qp.queries = (const double *)ix->ws_raw;
-        qp.q_stride = (int)(rec / 8);
-        qp.m = (uint32_t)m;
-        qp.k = k;
-        qp.r2 = radius_to_r2(radius);
-        qp.idx_out = idx_out ? (int32_t *)(o + off_idx) : nullptr;
-        qp.d2_out = d2_out ? (double *)(o + off_d2) : nullptr;
-        qp.rgba_out = rgba_out ? (uint8_t *)(o + off_rgba) : nullptr;
-        qp.normal_out = normal_out ? (float *)(o + off_nrm) : nullptr;
-        qp.in_flag = in_flag; qp.out_flag = out_flag; qp.done_count = done; qp.stream_err = err;
-        qp.epoch = epoch; qp.chunk = (uint32_t)chunk;
-        PT_TRY(launch_query(ix, qp, s));
-        PT_TRY(launch_stream_finish(out_flag, n_chunks, epoch, s));
-        // 3. the results, chunk by chunk, as soon as the kernel has released them
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            const size_t c0 = (size_t)c * chunk, cm = m - c0 < chunk ? m - c0 : chunk;
-            if (g_wait32(s_out, (unsigned long long)(uintptr_t)(out_flag + c), epoch, 1 /* EQ */) != 0) return PT_ERR_CUDA;
-            if (d2_out) PT_CUDA(cudaMemcpyAsync(d2_out + c0 * k, (double *)(o + off_d2) + c0 * k, cm * k * 8, cudaMemcpyDeviceToHost, s_out));
-            if (idx_out) PT_CUDA(cudaMemcpyAsync(idx_out + c0 * k, (int32_t *)(o + off_idx) + c0 * k, cm * k * 4, cudaMemcpyDeviceToHost, s_out));
-            if (normal_out) PT_CUDA(cudaMemcpyAsync(normal_out + c0 * 3, (float *)(o + off_nrm) + c0 * 3, cm * 12, cudaMemcpyDeviceToHost, s_out));
-            if (rgba_out) PT_CUDA(cudaMemcpyAsync(rgba_out + c0 * 4, (uint8_t *)(o + off_rgba) + c0 * 4, cm * 4, cudaMemcpyDeviceToHost, s_out));
-        }
-        PT_CUDA(cudaEventRecord(ix->cev[0], s_in));
-        PT_CUDA(cudaEventRecord(ix->cev[1], s_out));
-        PT_CUDA(cudaStreamWaitEvent(s, ix->cev[0], 0));
-        PT_CUDA(cudaStreamWaitEvent(s, ix->cev[1], 0));
-        PT_CUDA(cudaMemcpyAsync(&h_err, err, sizeof h_err, cudaMemcpyDeviceToHost, s));
-        PT_CUDA(cudaEventRecord(ix->ev[3], s));
-        return PT_OK;
-    };
-    int rc = issue();
-    if (rc != PT_OK) {
-        // unblock anything that may wait on a flag that will never be written, then drain
-        for (uint32_t c = 0; c < n_chunks; ++c) g_write32(s_in, (unsigned long long)(uintptr_t)(in_flag + c), epoch, 0);
-        launch_stream_finish(out_flag, n_chunks, epoch, s);
-        cudaStreamSynchronize(s_in); cudaStreamSynchronize(s); cudaStreamSynchronize(s_out);
-        cudaGetLastError();
-        return rc;
-    }
-    PT_CUDA(cudaStreamSynchronize(s));
-    if (h_err) return PT_ERR_CUDA;
-    ix->last_h2d_ms = 0.f;
     ix->last_d2h_ms = 0.f;
     cudaEventElapsedTime(&ix->last_query_ms, ix->ev[0], ix->ev[3]);
     return PT_OK;

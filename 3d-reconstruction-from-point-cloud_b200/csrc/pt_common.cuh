@@ -114,15 +114,7 @@ struct QueryParams {
     const uint32_t *qlist;     // optional: the launch answers samples qlist[0 .. *qcount) only
     const uint32_t *qcount;
     uint32_t        qlist_min; // list mode: do nothing unless *qcount >= qlist_min
-    const double  *queries;    // m records of q_stride doubles, coordinates first
-    int            q_stride;   // 3: packed xyz; 10: the reference's 80-byte Point records as uploaded
-    // streamed host-buffer call (pt_api.cu host_query_streamed): the samples arrive chunk by
-    // chunk while the grid kernel already runs, and finished chunks leave while it still runs
-    const uint32_t *in_flag;   // [chunk c] == epoch once the samples of chunk c are in device memory
-    uint32_t       *done_count;// [chunk c] samples of chunk c answered by the grid kernel
-    uint32_t       *out_flag;  // [chunk c] := epoch when every sample of chunk c has been answered
-    uint32_t       *stream_err;// set when a wait for in_flag timed out
-    uint32_t        epoch, chunk;
+    const double  *queries;    // m * 3
     const double  *r2_per_query;
     uint32_t       m;
     int            k;

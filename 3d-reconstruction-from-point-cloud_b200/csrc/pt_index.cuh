@@ -32,8 +32,6 @@ struct pt_index {
     void  *ws_raw = nullptr;   size_t ws_raw_bytes = 0;    // uploaded 80-byte query records
     void  *ws_q = nullptr;     size_t ws_q_bytes = 0;      // m*3 doubles
     void  *ws_out = nullptr;   size_t ws_out_bytes = 0;    // idx | d2 | rgba | normal
-    uint32_t *ws_flags = nullptr; size_t ws_flags_bytes = 0; // streamed calls: in | out | done | err per chunk
-    uint32_t stream_epoch = 0;                              // bumped per streamed call (flags never need a reset)
     cudaStream_t cs[16]{};                                  // chunk streams of the host-buffer API
     cudaEvent_t  cev[16]{};
 };
@@ -79,7 +77,6 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
 int unpack_queries_aos(const void *raw80_dev, size_t m, double *xyz_dev, cudaStream_t s);
 
 int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s);
-int launch_stream_finish(uint32_t *out_flag, uint32_t n_chunks, uint32_t epoch, cudaStream_t s);
 // Stream-ordered allocation from the library's PRIVATE memory pool of the current device (the
 // application's default pool is never touched); release with cudaFreeAsync.
 int pool_alloc(void **p, size_t bytes, cudaStream_t s);
@@ -125,7 +122,6 @@ int  opt_grid();
 int  opt_grid_tma();
 int  opt_sort_bits();
 size_t opt_pool_keep_bytes();
-int  opt_host_stream();
 int  debug_stats(unsigned long long *out16, int reset);
 
 }  // namespace pt

@@ -241,9 +241,9 @@ __device__ __forceinline__ void warp_query(const QueryParams &P, uint32_t q, uns
                                            float (*s_lb)[32])
 {
     const int k = P.k;
-    const double qx = __ldg(P.queries + (size_t)P.q_stride * q);
-    const double qy = __ldg(P.queries + (size_t)P.q_stride * q + 1);
-    const double qz = __ldg(P.queries + (size_t)P.q_stride * q + 2);
+    const double qx = __ldg(P.queries + 3 * (size_t)q);
+    const double qy = __ldg(P.queries + 3 * (size_t)q + 1);
+    const double qz = __ldg(P.queries + 3 * (size_t)q + 2);
     const float qdn[3] = {__double2float_rd(qx), __double2float_rd(qy), __double2float_rd(qz)};
     const float qup[3] = {__double2float_ru(qx), __double2float_ru(qy), __double2float_ru(qz)};
     const double r2 = P.r2_per_query ? __ldg(P.r2_per_query + q) : P.r2;
@@ -467,14 +467,6 @@ int launch_query(pt_index *ix, const QueryParams &qp_in, cudaStream_t s)
         return PT_OK;
     }
     return ix->coord_f64 ? launch_chain<PointD>(ix, qp, variant, s) : launch_chain<PointF>(ix, qp, variant, s);
-}
-
-int launch_stream_finish(uint32_t *out_flag, uint32_t n_chunks, uint32_t epoch, cudaStream_t s)
-{
-    stream_finish_kernel<<<1, 256, 0, s>>>(out_flag, n_chunks, epoch);
-    count_launch();
-    PT_CUDA(cudaGetLastError());
-    return PT_OK;
 }
 
 // ---- K5: merge per-slab candidate lists (multi-GPU exchange epilogue) -------------------------

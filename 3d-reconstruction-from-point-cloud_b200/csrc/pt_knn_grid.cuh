@@ -374,7 +374,7 @@ __device__ __forceinline__ int grid_attempt(const QueryParams &P, const GridTabl
 }
 
 template <typename PT, bool TMA>
-__device__ __forceinline__ bool grid_sample(const QueryParams &P, uint32_t s, double qx, double qy,
+__device__ __forceinline__ void grid_sample(const QueryParams &P, uint32_t s, double qx, double qy,
                                             double qz, unsigned lane, PT *cand, uint32_t bar,
                                             uint32_t &phase, uint32_t *ovf_count, uint32_t *ovf_list)
 {
@@ -435,7 +435,7 @@ __device__ __forceinline__ bool grid_sample(const QueryParams &P, uint32_t s, do
     if (!done) {
         PT_GSTAT(15, 1);
         if (lane == 0) ovf_list[atomicAdd(ovf_count, 1u)] = s;
-        return false;
+        return;
     }
 
     // ---- outputs: lane r holds the r-th neighbour ------------------------------------------------
@@ -450,13 +450,13 @@ __device__ __forceinline__ bool grid_sample(const QueryParams &P, uint32_t s, do
         if (P.d2_out) P.d2_out[o] = d;
         if (P.cand_out) store_cand(P.cand_out + o, d, gid, at);
     }
-    if (!want_blend) return true;
+    if (!want_blend) return;
     uint8_t *ro = P.rgba_out ? P.rgba_out + 4 * (size_t)s : nullptr;
     float *no = P.normal_out ? P.normal_out + 3 * (size_t)s : nullptr;
     const int cnt = __popc(__ballot_sync(0xffffffffu, has));
     if (cnt == 0) {
         if (lane == 0) store_empty_blend(ro, no);
-        return true;
+        return;
     }
     // frozen blend: per-neighbour terms in parallel, the sequential sums
     // one component per lane over a [7][32] tile that reuses the staging area
@@ -509,7 +509,6 @@ __device__ __forceinline__ bool grid_sample(const QueryParams &P, uint32_t s, do
     if (lane == 0 && ro) *reinterpret_cast<uchar4 *>(ro) = make_uchar4((unsigned char)cr, (unsigned char)cg, (unsigned char)cb, 255);
     if (lane >= 4 && lane < 7 && no)
         no[lane - 4] = (len > 0.0 && len < INFINITY) ? __double2float_rn(quo) : 0.0f;
-    return true;
 }
 
 #ifndef PT_GRID_MIN_BLOCKS
@@ -532,61 +531,20 @@ knn_grid_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     const uint32_t n_warps = gridDim.x * GRID_WARPS;
     uint32_t s = blockIdx.x * GRID_WARPS + wib;
     if (s >= P.m) return;
-    // Streamed calls: the coordinates of sample i may still be on their way (H2D copy of chunk
-    // i / chunk, followed in stream order by a write of `epoch` to in_flag[chunk]).  They are
-    // then read with a cache-bypassing load: the buffer is written while this kernel runs.
-    auto load_q = [&](uint32_t i, double &x, double &y, double &z) {
-        const double *rec = P.queries + (size_t)P.q_stride * i;
-        if (P.in_flag) {
-            const volatile uint32_t *f = P.in_flag + i / P.chunk;
-            if (*f != P.epoch) {
-                const long long t0 = clock64();
-                while (*f != P.epoch) {
-                    __nanosleep(500);
-                    if (clock64() - t0 > 8000000000ll) {      // ~4 s: the copy never came
-                        if (lane == 0) atomicExch(P.stream_err, 1u);
-                        x = y = z = 0.0;
-                        return false;
-                    }
-                }
-            }
-            __threadfence();
-            x = __ldcv(rec); y = __ldcv(rec + 1); z = __ldcv(rec + 2);
-        } else {
-            x = __ldg(rec); y = __ldg(rec + 1); z = __ldg(rec + 2);
-        }
-        return true;
-    };
-    double qx, qy, qz;
-    if (!load_q(s, qx, qy, qz)) return;
+    double qx = __ldg(P.queries + 3 * (size_t)s), qy = __ldg(P.queries + 3 * (size_t)s + 1),
+           qz = __ldg(P.queries + 3 * (size_t)s + 2);
     while (s < P.m) {
         // the next sample's coordinates are fetched while this one is answered
         const uint32_t sn = s + n_warps;
         double nx = 0.0, ny = 0.0, nz = 0.0;
-        if (sn > s && sn < P.m && !load_q(sn, nx, ny, nz)) return;
-        const bool answered = grid_sample<PT, TMA>(P, s, qx, qy, qz, lane, cand, bar, phase, ovf_count, ovf_list);
-        if (P.out_flag && answered) {
-            // every lane's result stores are visible device-wide before the chunk's count moves
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t c = s / P.chunk;
-                const uint32_t size = min(P.chunk, P.m - c * P.chunk);
-                if (atomicAdd(P.done_count + c, 1u) + 1u == size) {
-                    __threadfence();
-                    *reinterpret_cast<volatile uint32_t *>(P.out_flag + c) = P.epoch;
-                }
-            }
+        if (sn < P.m) {
+            nx = __ldg(P.queries + 3 * (size_t)sn);
+            ny = __ldg(P.queries + 3 * (size_t)sn + 1);
+            nz = __ldg(P.queries + 3 * (size_t)sn + 2);
         }
-        if (sn <= s) break;                      // index overflow guard (m close to 2^32)
+        grid_sample<PT, TMA>(P, s, qx, qy, qz, lane, cand, bar, phase, ovf_count, ovf_list);
         s = sn; qx = nx; qy = ny; qz = nz;
     }
-}
-
-// End of a streamed launch chain: whatever the second-stage kernels answered is final now too.
-__global__ void stream_finish_kernel(uint32_t *out_flag, uint32_t n_chunks, uint32_t epoch)
-{
-    for (uint32_t c = threadIdx.x; c < n_chunks; c += blockDim.x) out_flag[c] = epoch;
 }
 
 static inline size_t grid_kernel_smem(size_t rec_bytes)

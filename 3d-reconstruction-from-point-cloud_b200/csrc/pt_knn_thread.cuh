@@ -148,9 +148,9 @@ knn_thread_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
 
     double qx = 0, qy = 0, qz = 0, r2 = 0;
     if (live) {
-        qx = __ldg(P.queries + (size_t)P.q_stride * q);
-        qy = __ldg(P.queries + (size_t)P.q_stride * q + 1);
-        qz = __ldg(P.queries + (size_t)P.q_stride * q + 2);
+        qx = __ldg(P.queries + 3 * (size_t)q);
+        qy = __ldg(P.queries + 3 * (size_t)q + 1);
+        qz = __ldg(P.queries + 3 * (size_t)q + 2);
         r2 = P.r2_per_query ? __ldg(P.r2_per_query + q) : P.r2;
     }
     float bound = __double2float_ru(r2);

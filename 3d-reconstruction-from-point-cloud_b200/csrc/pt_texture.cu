@@ -328,7 +328,7 @@ static int texture_render_impl(pt_index *ix, const void *vertices, size_t n_vert
         qp.pts = ix->pts; qp.attrs = ix->attrs; qp.ids = nullptr; qp.pyr = ix->pyr;
         qp.n = ix->n; qp.n_leaves = ix->n_leaves; qp.w_levels = ix->w_levels; qp.t_levels = ix->t_levels;
         qp.pq_cap = opt_queue_cap();
-        qp.queries = d_xyz; qp.q_stride = 3; qp.m = (uint32_t)n_vertices; qp.k = k;
+        qp.queries = d_xyz; qp.m = (uint32_t)n_vertices; qp.k = k;
         qp.r2 = (!(radius >= 0.0) || std::isinf(radius)) ? INFINITY : radius * radius;
         qp.idx_out = d_idx;
         if ((rc = launch_query(ix, qp, s)) != PT_OK) break;

@@ -240,9 +240,7 @@ int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, 
  * "pool_keep_mb" (build temporaries kept cached in the library's private memory pool after a
  * build or a free, default 2048: a rebuild of a larger index maps fresh memory again),
  * "sort" (1 hand-written radix sort [default], 0 cub), "host_chunks" (pipeline chunks of the
- * host-buffer API, default 8), "host_stream" (1 [default]: host-buffer calls of >= 65536 samples run
- * as ONE kernel launch that consumes the chunks as their H2D copies land and releases finished
- * chunks to the D2H copies while it still runs; 0: one launch per chunk), "queue_cap" (tests: per-sample traversal queue entries, at most
+ * host-buffer API, default 8), "queue_cap" (tests: per-sample traversal queue entries, at most
  * the compiled 12), "verbose", "smem_pad" (diagnosis). */
 int pt_set_option(const char *name, int value);
 int pt_get_option(const char *name, int *value);

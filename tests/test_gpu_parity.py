@@ -37,7 +37,6 @@ def _default_options(pkg):
     pkg.set_option("queue_cap", 1 << 20)  # the compiled capacity
     pkg.set_option("order", 1)            # Hilbert order + cell tables (the default)
     pkg.set_option("grid_tma", 1)
-    pkg.set_option("host_stream", 1)
 
 
 # (knn_variant, order): grid / thread / warp / scan kernel x Morton, Hilbert, Hilbert + kd
@@ -446,36 +445,3 @@ def test_concurrent_launches_on_two_streams(variant, pkg, pto, torch_cuda):
         for (_, ref), o in zip(parts, outs):
             assert np.array_equal(o.cpu().numpy(), ref), (variant, rep)
     tree.close()
-
-
-@pytest.mark.parametrize("k,radius", [(8, None), (16, 0.5)])
-def test_streamed_host_call_equals_chunked_and_oracle(k, radius, pkg, pto, torch_cuda):
-    """Host-buffer calls of >= 65536 samples run as one streamed launch (chunks consumed as their
-    H2D copies land, finished chunks released to the D2H copies while the kernel still runs).
-    Same results as the per-chunk launches and as the oracle, from pageable and pinned buffers,
-    repeatedly (the flags are epoch-stamped, never reset)."""
-    torch = torch_cuda
-    P = pkg.synth.cloud_host(400_000, seed=51, side=90.0)
-    V = pkg.synth.samples_host(270, side=90.0)           # 72 900 samples
-    ref_idx, ref_d2 = pto.KdTree(P).knn(V, k, radius=-1.0 if radius is None else radius)
-    ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
-    with pkg.Tree(P) as tree:
-        for stream in (1, 0, 1, 1):
-            pkg.set_option("host_stream", stream)
-            out = tree.transfer(V, k, radius=radius, want_idx=True, want_d2=True)
-            assert np.array_equal(out["idx"], ref_idx), stream
-            assert np.array_equal(out["d2"], ref_d2), stream
-            _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
-        pkg.set_option("host_stream", 1)
-        idx, d2 = tree.knn(V, k, radius=radius)
-        assert np.array_equal(idx, ref_idx) and np.array_equal(d2, ref_d2)
-        # pinned caller buffers
-        m = len(V)
-        qpin = torch.from_numpy(V.view(np.uint8).reshape(m, 80)).pin_memory()
-        o = {"idx": torch.empty((m, k), dtype=torch.int32).pin_memory().numpy(),
-             "rgba": torch.empty((m, 4), dtype=torch.uint8).pin_memory().numpy(),
-             "normal": torch.empty((m, 3), dtype=torch.float32).pin_memory().numpy()}
-        for _ in range(3):
-            tree.transfer(qpin.numpy().view(pkg.POINT_DTYPE).reshape(-1), k, radius=radius, out=o)
-            assert np.array_equal(o["idx"], ref_idx)
-            _check_blend(o["rgba"], o["normal"], ref_rgba, ref_nrm)
