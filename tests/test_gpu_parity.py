@@ -445,3 +445,31 @@ def test_concurrent_launches_on_two_streams(variant, pkg, pto, torch_cuda):
         for (_, ref), o in zip(parts, outs):
             assert np.array_equal(o.cpu().numpy(), ref), (variant, rep)
     tree.close()
+
+
+@pytest.mark.parametrize("k,radius", [(8, None), (16, 0.5)])
+def test_large_host_call_equals_oracle(k, radius, pkg, pto, torch_cuda):
+    """A host-buffer call large enough for the chunk pipeline (8 chunks on 8 streams): same
+    results as the oracle from pageable and from pinned caller buffers, repeatedly."""
+    torch = torch_cuda
+    P = pkg.synth.cloud_host(400_000, seed=51, side=90.0)
+    V = pkg.synth.samples_host(270, side=90.0)           # 72 900 samples
+    ref_idx, ref_d2 = pto.KdTree(P).knn(V, k, radius=-1.0 if radius is None else radius)
+    ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+    with pkg.Tree(P) as tree:
+        for chunks in (8, 1, 3):
+            pkg.set_option("host_chunks", chunks)
+            out = tree.transfer(V, k, radius=radius, want_idx=True, want_d2=True)
+            assert np.array_equal(out["idx"], ref_idx), chunks
+            assert np.array_equal(out["d2"], ref_d2), chunks
+            _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
+        pkg.set_option("host_chunks", 8)
+        m = len(V)
+        qpin = torch.from_numpy(V.view(np.uint8).reshape(m, 80)).pin_memory()
+        o = {"idx": torch.empty((m, k), dtype=torch.int32).pin_memory().numpy(),
+             "rgba": torch.empty((m, 4), dtype=torch.uint8).pin_memory().numpy(),
+             "normal": torch.empty((m, 3), dtype=torch.float32).pin_memory().numpy()}
+        for _ in range(3):
+            tree.transfer(qpin.numpy().view(pkg.POINT_DTYPE).reshape(-1), k, radius=radius, out=o)
+            assert np.array_equal(o["idx"], ref_idx)
+            _check_blend(o["rgba"], o["normal"], ref_rgba, ref_nrm)
