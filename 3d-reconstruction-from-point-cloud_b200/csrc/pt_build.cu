@@ -719,37 +719,48 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
     *xyz_out = nullptr;
     *representable = true;
     if (n == 0) return PT_OK;
+    // one exit path: whatever was acquired before a failure is released (ix->attrs belongs to the
+    // handle and is released with it)
     double *xyz = nullptr;
-    PT_CUDA(cudaMalloc(&xyz, sizeof(double) * 3 * n));
-    PT_CUDA(cudaMalloc(&ix->attrs, sizeof(pt_attr) * n));
     unsigned int *flag = nullptr;
-    PT_CUDA(cudaMalloc(&flag, sizeof(unsigned int)));
-    PT_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), s));
+    Raw80 *stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    unsigned int h_flag = 0;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
     // chunked upload through two device staging buffers
     const size_t chunk = (size_t)1 << 22;  // 4 Mi records = 320 MiB per buffer
-    size_t cap = n < chunk ? n : chunk;
-    Raw80 *stage[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
-    PT_CUDA(cudaMalloc(&stage[0], sizeof(Raw80) * cap));
-    PT_CUDA(cudaMalloc(&stage[1], sizeof(Raw80) * cap));
-    PT_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
-    PT_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
-    int b = 0;
-    for (size_t off = 0; off < n; off += cap, b ^= 1) {
-        size_t cnt = n - off < cap ? n - off : cap;
-        PT_CUDA(cudaEventSynchronize(done[b]));
-        PT_CUDA(cudaMemcpyAsync(stage[b], (const char *)points + off * sizeof(Raw80),
-                                cnt * sizeof(Raw80), cudaMemcpyHostToDevice, s));
-        unpack_points_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(stage[b], (uint32_t)cnt,
-                                                            xyz + 3 * off, ix->attrs + off, flag);
-        count_launch();
-        PT_CUDA(cudaEventRecord(done[b], s));
+    const size_t cap = n < chunk ? n : chunk;
+    if (ok(cudaMalloc(&xyz, sizeof(double) * 3 * n)) && ok(cudaMalloc(&ix->attrs, sizeof(pt_attr) * n)) &&
+        ok(cudaMalloc(&flag, sizeof(unsigned int))) && ok(cudaMemsetAsync(flag, 0, sizeof(unsigned int), s)) &&
+        ok(cudaMalloc(&stage[0], sizeof(Raw80) * cap)) && ok(cudaMalloc(&stage[1], sizeof(Raw80) * cap)) &&
+        ok(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)) &&
+        ok(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming))) {
+        int b = 0;
+        for (size_t off = 0; off < n && e == cudaSuccess; off += cap, b ^= 1) {
+            const size_t cnt = n - off < cap ? n - off : cap;
+            if (!ok(cudaEventSynchronize(done[b]))) break;
+            if (!ok(cudaMemcpyAsync(stage[b], (const char *)points + off * sizeof(Raw80), cnt * sizeof(Raw80),
+                                    cudaMemcpyHostToDevice, s)))
+                break;
+            unpack_points_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(stage[b], (uint32_t)cnt, xyz + 3 * off,
+                                                                ix->attrs + off, flag);
+            count_launch();
+            ok(cudaEventRecord(done[b], s));
+        }
+        if (e == cudaSuccess) ok(cudaMemcpyAsync(&h_flag, flag, sizeof h_flag, cudaMemcpyDeviceToHost, s));
     }
-    unsigned int h_flag = 0;
-    PT_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof h_flag, cudaMemcpyDeviceToHost, s));
-    PT_CUDA(cudaStreamSynchronize(s));
+    const cudaError_t es = cudaStreamSynchronize(s);      // nothing is still reading `points` after this
+    if (e == cudaSuccess) e = es;
     cudaFree(stage[0]); cudaFree(stage[1]); cudaFree(flag);
-    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    if (done[0]) cudaEventDestroy(done[0]);
+    if (done[1]) cudaEventDestroy(done[1]);
+    if (e != cudaSuccess) {
+        cudaFree(xyz);
+        cudaGetLastError();
+        if (verbose()) fprintf(stderr, "[points_transfer] ingest: %s\n", cudaGetErrorString(e));
+        return map_cuda_error(e);
+    }
     *representable = h_flag == 0;
     *xyz_out = xyz;
     return PT_OK;
