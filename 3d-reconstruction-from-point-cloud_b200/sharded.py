@@ -66,21 +66,40 @@ class ShardedTransfer:
         self.last_counts = counts
         return out
 
-    def transfer_host(self, q_host, out_host, radius=None, scratch=None):
+    def transfer_host(self, q_host, out_host, radius=None, scratch=None, pieces=2):
         """Host-buffer form: q_host float64 [m,3] (pinned), out_host dict of (pinned) host tensors.
-        Returns after the results have landed."""
+        The batch runs as ``pieces`` consecutive sharded steps so that the D2H copy of one piece's
+        results (80 bytes per sample, the largest item of the call) overlaps the next piece's
+        step; every rank must use the same ``pieces``.  Returns after the results have landed."""
         m = q_host.shape[0]
+        cuda = self.dev.type == "cuda"
         if scratch is None or scratch["q"].shape[0] != m:
             scratch = {"q": torch.empty((m, 3), dtype=torch.float64, device=self.dev),
                        "idx": torch.empty((m, self.k), dtype=torch.int32, device=self.dev),
                        "rgba": torch.empty((m, 4), dtype=torch.uint8, device=self.dev),
                        "normal": torch.empty((m, 3), dtype=torch.float32, device=self.dev)}
+            if cuda:
+                scratch["copy_stream"] = torch.cuda.Stream(device=self.dev)
+        pieces = max(1, min(int(pieces), max(m, 1)))
+        step = -(-m // pieces)
         scratch["q"].copy_(q_host, non_blocking=True)
-        self.transfer(scratch["q"], scratch, radius=radius)
-        for name in ("idx", "rgba", "normal"):
-            out_host[name].copy_(scratch[name], non_blocking=True)
-        if self.dev.type == "cuda":
-            torch.cuda.current_stream(self.dev).synchronize()
+        cur = torch.cuda.current_stream(self.dev) if cuda else None
+        for p in range(pieces):
+            lo, hi = p * step, min(m, (p + 1) * step)
+            part = {n: scratch[n][lo:hi] for n in ("idx", "rgba", "normal")}
+            self.transfer(scratch["q"][lo:hi], part, radius=radius)
+            if cuda:
+                cs = scratch["copy_stream"]
+                cs.wait_stream(cur)
+                with torch.cuda.stream(cs):
+                    for n in ("idx", "rgba", "normal"):
+                        out_host[n][lo:hi].copy_(part[n], non_blocking=True)
+            else:
+                for n in ("idx", "rgba", "normal"):
+                    out_host[n][lo:hi].copy_(part[n])
+        if cuda:
+            cur.wait_stream(scratch["copy_stream"])
+            cur.synchronize()
         return scratch
 
     def validate(self):

@@ -56,6 +56,15 @@ def _worker(rank, world, port, halo, k, radius):
         assert np.array_equal(out["rgba"].numpy(), ref_rgba), f"rank {rank}: rgba"
         assert np.allclose(out["normal"].numpy(), ref_nrm, rtol=1e-5, atol=1e-7)
         assert st.stats()["routed_to_other_slabs"] > 0
+        # host-buffer form, in two and three pieces: same results
+        for pieces in (2, 3):
+            host = {"idx": torch.full((len(share), k), -7, dtype=torch.int32),
+                    "rgba": torch.zeros((len(share), 4), dtype=torch.uint8),
+                    "normal": torch.zeros((len(share), 3), dtype=torch.float32)}
+            st.transfer_host(q, host, radius=radius, pieces=pieces)
+            assert st.validate()
+            for name in ("idx", "rgba", "normal"):
+                assert torch.equal(host[name], out[name]), (pieces, name)
     finally:
         dist.destroy_process_group()
 
