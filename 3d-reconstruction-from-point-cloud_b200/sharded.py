@@ -66,11 +66,13 @@ class ShardedTransfer:
         self.last_counts = counts
         return out
 
-    def transfer_host(self, q_host, out_host, radius=None, scratch=None, pieces=2):
+    def transfer_host(self, q_host, out_host, radius=None, scratch=None, pieces=1):
         """Host-buffer form: q_host float64 [m,3] (pinned), out_host dict of (pinned) host tensors.
-        The batch runs as ``pieces`` consecutive sharded steps so that the D2H copy of one piece's
-        results (80 bytes per sample, the largest item of the call) overlaps the next piece's
-        step; every rank must use the same ``pieces``.  Returns after the results have landed."""
+        With ``pieces`` > 1 the batch runs as consecutive sharded steps so that the D2H copy of one
+        piece's results overlaps the next piece's step (every rank must use the same ``pieces``);
+        measured on 4 GPUs at cfg3 this LOSES (2.36 ms against 1.67 ms in one piece: every step
+        pays its four all_to_all and the small-launch inefficiency of the query kernel), hence the
+        default of one piece.  Returns after the results have landed."""
         m = q_host.shape[0]
         cuda = self.dev.type == "cuda"
         if scratch is None or scratch["q"].shape[0] != m:
