@@ -48,7 +48,8 @@ ABI_SYMBOLS = (
     "pt_index_get_info", "pt_index_fallback_counts", "pt_knn", "pt_transfer", "pt_texture_render", "pt_transfer_slab", "pt_index_build_device", "pt_query_device",
     "pt_merge_device", "pt_halo_route_device", "pt_halo_prepare_device",
     "pt_halo_merge_device", "pt_ghost_check_device", "pt_route_samples_device",
-    "pt_scatter_rows_device", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
+    "pt_scatter_rows_device", "pt_sharded_build", "pt_sharded_free", "pt_sharded_get_info", "pt_sharded_knn",
+    "pt_sharded_transfer", "pt_texture_render_lists", "pt_set_option", "pt_get_option", "pt_debug_stats", "pt_kernel_launch_count",
 )
 # ... and include/pt_synth.h (bench / test scaffolding, its own library)
 SYNTH_SYMBOLS = ("pt_synth_cloud_device", "pt_synth_samples_device", "pt_synth_pack_points_device",
@@ -80,6 +81,17 @@ class IndexInfo(ctypes.Structure):
 class TextureStats(ctypes.Structure):
     _fields_ = [("triangles", ctypes.c_uint64), ("inside_points", ctypes.c_uint64),
                 ("knn_ms", ctypes.c_float), ("draw_ms", ctypes.c_float), ("pad_ms", ctypes.c_float)]
+
+
+class ShardedOpts(ctypes.Structure):
+    _fields_ = [("n_devices", ctypes.c_int), ("devices", ctypes.POINTER(ctypes.c_int)), ("halo", ctypes.c_double),
+                ("k_hint", ctypes.c_int), ("coord_mode", ctypes.c_int), ("reserved", ctypes.c_int * 8)]
+
+
+class ShardedInfo(ctypes.Structure):
+    _fields_ = [("n_slabs", ctypes.c_int), ("rebuilds", ctypes.c_int), ("halo", ctypes.c_double),
+                ("n_points", ctypes.c_uint64), ("slab_points", ctypes.c_uint64 * 64),
+                ("slab_ghosts", ctypes.c_uint64 * 64), ("slab_device", ctypes.c_int * 64)]
 
 
 class SynthParams(ctypes.Structure):
@@ -143,6 +155,19 @@ def lib():
     L.pt_route_samples_device.argtypes = [vp, sz, vp, i32, u32, vp, vp, vp, vp, vp]
     L.pt_scatter_rows_device.restype = i32
     L.pt_scatter_rows_device.argtypes = [vp, vp, sz, u32, vp, vp]
+    L.pt_sharded_build.restype = i32
+    L.pt_sharded_build.argtypes = [vp, sz, ctypes.POINTER(ShardedOpts), ctypes.POINTER(vp)]
+    L.pt_sharded_free.restype = i32
+    L.pt_sharded_free.argtypes = [vp]
+    L.pt_sharded_get_info.restype = i32
+    L.pt_sharded_get_info.argtypes = [vp, ctypes.POINTER(ShardedInfo)]
+    L.pt_sharded_knn.restype = i32
+    L.pt_sharded_knn.argtypes = [vp, vp, sz, i32, dbl, vp, vp]
+    L.pt_sharded_transfer.restype = i32
+    L.pt_sharded_transfer.argtypes = [vp, vp, sz, i32, dbl, vp, vp, vp, vp]
+    L.pt_texture_render_lists.restype = i32
+    L.pt_texture_render_lists.argtypes = [vp, sz, vp, sz, vp, sz, vp, i32, i32, i32, i32, vp,
+                                          ctypes.POINTER(TextureStats)]
     L.pt_set_option.restype = i32
     L.pt_set_option.argtypes = [ctypes.c_char_p, i32]
     L.pt_get_option.restype = i32
@@ -383,6 +408,75 @@ class Tree:
                                       int(rank), float(halo), idx_ptr, d2_ptr, rgba_ptr,
                                       normal_ptr, ctypes.byref(need)), "pt_transfer_slab")
         return need.value == 0
+
+
+class ShardedTree:
+    """The cloud sharded over several GPUs of one box by the C++ host (``pt_sharded_*``,
+    csrc/pt_sharded.cu): same calls as ``Tree``, ids index the caller's ``points``."""
+
+    def __init__(self, points, devices, halo=0.0, k_hint=20, coord_mode=COORD_AUTO):
+        self._points = _as_points(points, "points")          # must outlive the handle
+        self._h = ctypes.c_void_p()
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        o = ShardedOpts()
+        o.n_devices, o.devices, o.halo, o.k_hint, o.coord_mode = len(devices), devs, float(halo), int(k_hint), int(coord_mode)
+        _check(lib().pt_sharded_build(_np_ptr(self._points), self._points.shape[0], ctypes.byref(o),
+                                      ctypes.byref(self._h)), "pt_sharded_build")
+
+    def info(self):
+        i = ShardedInfo()
+        _check(lib().pt_sharded_get_info(self._h, ctypes.byref(i)), "pt_sharded_get_info")
+        n = i.n_slabs
+        return {"n_slabs": n, "rebuilds": i.rebuilds, "halo": i.halo, "slab_points": list(i.slab_points[:n]),
+                "slab_ghosts": list(i.slab_ghosts[:n]), "slab_device": list(i.slab_device[:n])}
+
+    def knn(self, queries, k, radius=None, want_d2=True):
+        q = _as_points(queries, "queries")
+        m = q.shape[0]
+        idx = np.empty((m, k), dtype=np.int32)
+        d2 = np.empty((m, k), dtype=np.float64) if want_d2 else None
+        _check(lib().pt_sharded_knn(self._h, _np_ptr(q), m, int(k), _radius(radius), _np_ptr(idx), _np_ptr(d2)),
+               "pt_sharded_knn")
+        return idx, d2
+
+    def transfer(self, queries, k, radius=None, want_idx=True, want_d2=False):
+        q = _as_points(queries, "queries")
+        m = q.shape[0]
+        out = {"rgba": np.empty((m, 4), dtype=np.uint8), "normal": np.empty((m, 3), dtype=np.float32)}
+        if want_idx:
+            out["idx"] = np.empty((m, k), dtype=np.int32)
+        if want_d2:
+            out["d2"] = np.empty((m, k), dtype=np.float64)
+        _check(lib().pt_sharded_transfer(self._h, _np_ptr(q), m, int(k), _radius(radius), _np_ptr(out.get("idx")),
+                                         _np_ptr(out.get("d2")), _np_ptr(out["rgba"]), _np_ptr(out["normal"])),
+               "pt_sharded_transfer")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().pt_sharded_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def texture_from_lists(points, vertices, faces, idx, resolution=8192, pad=True, device=0):
+    """``pt_texture_render_lists``: the texture stage for neighbour lists computed elsewhere."""
+    p, v = _as_points(points, "points"), _as_points(vertices, "vertices")
+    f = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    img = np.empty((resolution, resolution, 4), dtype=np.uint8)
+    st = TextureStats()
+    _check(lib().pt_texture_render_lists(_np_ptr(p), p.shape[0], _np_ptr(v), v.shape[0], _np_ptr(f), f.shape[0],
+                                         _np_ptr(idx), idx.shape[1], int(resolution), 1 if pad else 0, int(device),
+                                         _np_ptr(img), ctypes.byref(st)), "pt_texture_render_lists")
+    return img, {"triangles": int(st.triangles), "inside_points": int(st.inside_points)}
 
 
 class K_neighbor_search:

@@ -135,9 +135,27 @@ __device__ void tx_draw_triangle(const TexVertex &t0, const TexVertex &t1, const
     }
 }
 
-template <typename PT>
+// where the position of cloud point `id` (original index) comes from
+template <typename PT> struct PosSorted {      // an index: sorted records + inverse permutation
+    const PT *pts;
+    const uint32_t *inv;
+    __device__ __forceinline__ void get(int id, double x[3]) const
+    {
+        const PT rec = pts[inv[id]];
+        x[0] = (double)rec.x; x[1] = (double)rec.y; x[2] = (double)rec.z;
+    }
+};
+struct PosPlain {                               // n x 3 doubles in original order
+    const double *xyz;
+    __device__ __forceinline__ void get(int id, double x[3]) const
+    {
+        x[0] = xyz[3 * (size_t)id]; x[1] = xyz[3 * (size_t)id + 1]; x[2] = xyz[3 * (size_t)id + 2];
+    }
+};
+
+template <typename POS>
 __global__ void __launch_bounds__(64)
-tex_face_kernel(const PT *pts, const uint32_t *inv_perm, const pt_attr *attrs, const MeshVertex *mv,
+tex_face_kernel(const POS pos, uint32_t n_points, const pt_attr *attrs, const MeshVertex *mv,
                 const int32_t *idx, int k, const int32_t *faces, uint32_t n_faces, uint32_t n_vertices,
                 int res, unsigned long long *canvas, unsigned long long *stats)
 {
@@ -156,7 +174,7 @@ tex_face_kernel(const PT *pts, const uint32_t *inv_perm, const pt_attr *attrs, c
     for (int c = 0; c < 3; ++c)
         for (int j = 0; j < k; ++j) {
             const int id = idx[(size_t)vi[c] * k + j];
-            if (id < 0) continue;
+            if (id < 0 || (uint32_t)id >= n_points) continue;
             bool seen = false;
             for (int e = 0; e < n_nb; ++e) seen |= nb[e] == id;
             if (!seen) nb[n_nb++] = id;
@@ -193,8 +211,8 @@ tex_face_kernel(const PT *pts, const uint32_t *inv_perm, const pt_attr *attrs, c
         V[c].r = tv[c].r; V[c].g = tv[c].g; V[c].b = tv[c].b;
     }
     for (int e = 0; e < n_nb; ++e) {
-        const PT rec = pts[inv_perm[nb[e]]];
-        const double x[3] = {(double)rec.x, (double)rec.y, (double)rec.z};
+        double x[3];
+        pos.get(nb[e], x);
         const V2 xp = tx_to_2d(x, R, n, b1, b2);
         double bc[3];
         tx_tri_coords(P[0], P[1], P[2], xp, bc);
@@ -282,10 +300,13 @@ tex_dilate_v_pad_kernel(const uint32_t *tex, const uint32_t *tmp, int res, uint3
 
 static inline unsigned tcdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-template <typename PT>
-static int texture_render_impl(pt_index *ix, const void *vertices, size_t n_vertices, const int32_t *faces,
-                               size_t n_faces, int k, double radius, int res, int pad, uint8_t *bgra_out,
-                               pt_texture_stats *st)
+// Mesh upload + (optionally) the neighbour search + face kernel + post-process.  `ix` gives the
+// stream, the query kernels (when d_idx_given is null) and the attribute array.
+template <typename POS>
+static int texture_pipeline(pt_index *ix, POS pos, uint32_t n_points, const pt_attr *attrs, bool search,
+                            const int32_t *idx_host, const void *vertices, size_t n_vertices,
+                            const int32_t *faces, size_t n_faces, int k, double radius, int res, int pad,
+                            uint8_t *bgra_out, pt_texture_stats *st)
 {
     cudaStream_t s = ix->stream;
     const size_t n_pix = (size_t)res * res;
@@ -309,11 +330,6 @@ static int texture_render_impl(pt_index *ix, const void *vertices, size_t n_vert
             rc = PT_ERR_OUT_OF_MEMORY;
             break;
         }
-        if (!ix->inv_perm && ix->n) {            // original index -> position in the sorted cloud, built once
-            if (fail(cudaMalloc(&ix->inv_perm, sizeof(uint32_t) * (size_t)ix->n))) break;
-            tex_inverse_perm_kernel<PT><<<tcdiv(ix->n, 256), 256, 0, s>>>((const PT *)ix->pts, ix->n, ix->inv_perm);
-            count_launch();
-        }
         if (fail(cudaEventRecord(ev[0], s))) break;
         if (fail(cudaMemcpyAsync(d_raw, vertices, sizeof(Raw80t) * n_vertices, cudaMemcpyHostToDevice, s))) break;
         if (fail(cudaMemcpyAsync(d_faces, faces, sizeof(int32_t) * 3 * n_faces, cudaMemcpyHostToDevice, s))) break;
@@ -323,20 +339,24 @@ static int texture_render_impl(pt_index *ix, const void *vertices, size_t n_vert
             tex_unpack_vertices_kernel<<<tcdiv(n_vertices, 256), 256, 0, s>>>(d_raw, (uint32_t)n_vertices, d_mv, d_xyz);
             count_launch();
         }
-        // the neighbour search of every UNIQUE vertex (the reference searches 3 x per face, :474)
-        QueryParams qp{};
-        qp.pts = ix->pts; qp.attrs = ix->attrs; qp.ids = nullptr; qp.pyr = ix->pyr;
-        qp.n = ix->n; qp.n_leaves = ix->n_leaves; qp.w_levels = ix->w_levels; qp.t_levels = ix->t_levels;
-        qp.pq_cap = opt_queue_cap();
-        qp.queries = d_xyz; qp.m = (uint32_t)n_vertices; qp.k = k;
-        qp.r2 = (!(radius >= 0.0) || std::isinf(radius)) ? INFINITY : radius * radius;
-        qp.idx_out = d_idx;
-        if ((rc = launch_query(ix, qp, s)) != PT_OK) break;
+        if (search) {
+            // the neighbour search of every UNIQUE vertex (the reference searches 3 x per face, :474)
+            QueryParams qp{};
+            qp.pts = ix->pts; qp.attrs = ix->attrs; qp.ids = nullptr; qp.pyr = ix->pyr;
+            qp.n = ix->n; qp.n_leaves = ix->n_leaves; qp.w_levels = ix->w_levels; qp.t_levels = ix->t_levels;
+            qp.pq_cap = opt_queue_cap();
+            qp.queries = d_xyz; qp.m = (uint32_t)n_vertices; qp.k = k;
+            qp.r2 = (!(radius >= 0.0) || std::isinf(radius)) ? INFINITY : radius * radius;
+            qp.idx_out = d_idx;
+            if ((rc = launch_query(ix, qp, s)) != PT_OK) break;
+        } else if (n_vertices) {
+            if (fail(cudaMemcpyAsync(d_idx, idx_host, sizeof(int32_t) * n_vertices * k, cudaMemcpyHostToDevice, s))) break;
+        }
         if (fail(cudaEventRecord(ev[1], s))) break;
         if (n_faces) {
-            tex_face_kernel<PT><<<tcdiv(n_faces, 64), 64, 0, s>>>((const PT *)ix->pts, ix->inv_perm, ix->attrs, d_mv, d_idx, k,
-                                                               d_faces, (uint32_t)n_faces, (uint32_t)n_vertices, res,
-                                                               d_canvas, d_stats);
+            tex_face_kernel<POS><<<tcdiv(n_faces, 64), 64, 0, s>>>(pos, n_points, attrs, d_mv, d_idx, k, d_faces,
+                                                                (uint32_t)n_faces, (uint32_t)n_vertices, res, d_canvas,
+                                                                d_stats);
             count_launch();
         }
         tex_resolve_kernel<<<tcdiv(n_pix, 256), 256, 0, s>>>(d_canvas, n_pix, d_tex);
@@ -371,6 +391,21 @@ static int texture_render_impl(pt_index *ix, const void *vertices, size_t n_vert
     return rc;
 }
 
+template <typename PT>
+static int texture_render_index(pt_index *ix, const void *vertices, size_t n_vertices, const int32_t *faces,
+                                size_t n_faces, int k, double radius, int res, int pad, uint8_t *bgra_out,
+                                pt_texture_stats *st)
+{
+    if (!ix->inv_perm && ix->n) {            // original index -> position in the sorted cloud, built once
+        PT_CUDA(cudaMalloc(&ix->inv_perm, sizeof(uint32_t) * (size_t)ix->n));
+        tex_inverse_perm_kernel<PT><<<tcdiv(ix->n, 256), 256, 0, ix->stream>>>((const PT *)ix->pts, ix->n, ix->inv_perm);
+        count_launch();
+    }
+    PosSorted<PT> pos{(const PT *)ix->pts, ix->inv_perm};
+    return texture_pipeline(ix, pos, ix->n, ix->attrs, true, nullptr, vertices, n_vertices, faces, n_faces, k, radius,
+                            res, pad, bgra_out, st);
+}
+
 }  // namespace pt
 
 using namespace pt;
@@ -386,6 +421,38 @@ extern "C" int pt_texture_render(pt_index *ix, const void *vertices, size_t n_ve
     if (ix->ids) return PT_ERR_UNSUPPORTED;           // slab indexes answer with global ids
     if (!ix->attrs && ix->n) return PT_ERR_INVALID_ARG;
     PT_CUDA(cudaSetDevice(ix->device));
-    return ix->coord_f64 ? texture_render_impl<PointD>(ix, vertices, n_vertices, faces, n_faces, k, radius, resolution, pad, bgra_out, stats)
-                         : texture_render_impl<PointF>(ix, vertices, n_vertices, faces, n_faces, k, radius, resolution, pad, bgra_out, stats);
+    return ix->coord_f64 ? texture_render_index<PointD>(ix, vertices, n_vertices, faces, n_faces, k, radius, resolution, pad, bgra_out, stats)
+                         : texture_render_index<PointF>(ix, vertices, n_vertices, faces, n_faces, k, radius, resolution, pad, bgra_out, stats);
+}
+
+extern "C" int pt_texture_render_lists(const void *points, size_t n, const void *vertices, size_t n_vertices,
+                                       const int32_t *faces, size_t n_faces, const int32_t *idx, int k,
+                                       int resolution, int pad, int device, uint8_t *bgra_out,
+                                       pt_texture_stats *stats)
+{
+    if ((!points && n) || (!vertices && n_vertices) || (!faces && n_faces) || (!idx && n_vertices) || !bgra_out ||
+        resolution < 1 || resolution > 32768 || n >= 0x7fffffffull || n_vertices > 0x7ffffff0ull || n_faces >= (1ull << 24))
+        return PT_ERR_INVALID_ARG;
+    if (k < 1 || k > PT_MAX_K) return PT_ERR_UNSUPPORTED;
+    if (pt_device_count() == 0) return PT_ERR_NO_DEVICE;
+    if (device < 0) PT_CUDA(cudaGetDevice(&device));
+    PT_CUDA(cudaSetDevice(device));
+    // a bare handle: a stream plus the cloud's positions and attributes in original order
+    pt_index tmp;
+    tmp.device = device;
+    double *xyz = nullptr;
+    bool representable = true;
+    int rc = map_cuda_error(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
+    if (rc == PT_OK) rc = ingest_points_aos(&tmp, points, n, PT_COORD_AUTO, &xyz, &representable);
+    if (rc == PT_OK) {
+        PosPlain pos{xyz};
+        rc = texture_pipeline(&tmp, pos, (uint32_t)n, tmp.attrs, false, idx, vertices, n_vertices, faces, n_faces, k,
+                              -1.0, resolution, pad, bgra_out, stats);
+    }
+    if (tmp.stream) cudaStreamSynchronize(tmp.stream);
+    cudaFree(xyz);
+    cudaFree(tmp.attrs);
+    if (tmp.stream) cudaStreamDestroy(tmp.stream);
+    cudaGetLastError();
+    return rc;
 }

@@ -240,6 +240,7 @@ int main(int argc, char **argv)
     int K = 20;             // src/pointsTransfer.cpp:128
     double radius = -1.0;   // unbounded, as the reference
     int device = -1;
+    int n_gpus = 1;         // -g N: the cloud sharded into N x-slabs (pt_sharded_*), slab r on GPU r mod #GPUs
     int resolution = 8192;  // src/pointsTransfer.cpp:129
     std::string out_name = "texture.png";          // src/pointsTransfer.cpp:613
     std::string ply_name;                          // optional extra: the per-vertex blend as a PLY
@@ -251,15 +252,16 @@ int main(int argc, char **argv)
         else if (a == "-p" && i + 1 < argc) ply_name = argv[++i];
         else if (a == "-R" && i + 1 < argc) resolution = atoi(argv[++i]);
         else if (a == "-d" && i + 1 < argc) device = atoi(argv[++i]);
+        else if (a == "-g" && i + 1 < argc) n_gpus = atoi(argv[++i]);
         else pos_args.push_back(a);
     }
     if (pos_args.size() < 2) {
         std::cout << usage_str << std::endl;
         return 0;
     }
-    if (K < 1 || K > PT_MAX_K || resolution < 1 || resolution > 32768) {
+    if (K < 1 || K > PT_MAX_K || resolution < 1 || resolution > 32768 || n_gpus < 1 || n_gpus > 64) {
         // like every error path of the reference: a message, exit code 0
-        std::cerr << "-k must be 1.." << PT_MAX_K << " and -R 1..32768" << std::endl;
+        std::cerr << "-k must be 1.." << PT_MAX_K << ", -R 1..32768 and -g 1..64" << std::endl;
         return 0;
     }
     const std::string pc_file_name = pos_args[0], mesh_file_name = pos_args[1];
@@ -282,14 +284,25 @@ int main(int argc, char **argv)
     std::cout << "Read point set in: " << task_timer.time() << " seconds" << std::endl;
     task_timer.reset();
 
-    pt_build_opts opts;
-    memset(&opts, 0, sizeof opts);
-    opts.device = device;
-    opts.coord_mode = PT_COORD_AUTO;
     pt_index *index = nullptr;
-    int rc = pt_index_build(points.data(), points.size(), &opts, &index);
+    pt_sharded *sharded = nullptr;
+    int rc;
+    if (n_gpus > 1) {
+        pt_sharded_opts so;
+        memset(&so, 0, sizeof so);
+        so.n_devices = n_gpus;
+        so.k_hint = K;
+        so.coord_mode = PT_COORD_AUTO;
+        rc = pt_sharded_build(points.data(), points.size(), &so, &sharded);
+    } else {
+        pt_build_opts opts;
+        memset(&opts, 0, sizeof opts);
+        opts.device = device;
+        opts.coord_mode = PT_COORD_AUTO;
+        rc = pt_index_build(points.data(), points.size(), &opts, &index);
+    }
     if (rc != PT_OK) {
-        std::cerr << "pt_index_build failed: " << pt_status_string(rc) << std::endl;
+        std::cerr << "index build failed: " << pt_status_string(rc) << std::endl;
         return 0;
     }
     std::cout << "Built Kd tree in: " << task_timer.time() << " seconds" << std::endl;
@@ -299,6 +312,7 @@ int main(int argc, char **argv)
     if (!mesh.load(mesh_file_name)) {
         std::cerr << "Cannot read or find mesh file: " << mesh_file_name << std::endl;
         pt_index_free(index);
+        pt_sharded_free(sharded);
         return 0;
     }
     Header mh;
@@ -328,11 +342,25 @@ int main(int argc, char **argv)
     std::vector<uint8_t> texture((size_t)resolution * resolution * 4);
     pt_texture_stats ts;
     memset(&ts, 0, sizeof ts);
-    rc = pt_texture_render(index, vertices.data(), m, faces.data(), faces.size() / 3, K, radius, resolution, 1,
-                           texture.data(), &ts);
+    if (sharded) {
+        // sharded search (one host thread and one index per slab), then the face / texture stage on
+        // one GPU from the lists
+        std::vector<int32_t> nn(m * (size_t)K);
+        Timer knn_timer;
+        rc = pt_sharded_knn(sharded, vertices.data(), m, K, radius, nn.data(), nullptr);
+        const double knn_s = knn_timer.time();
+        if (rc == PT_OK)
+            rc = pt_texture_render_lists(points.data(), points.size(), vertices.data(), m, faces.data(), faces.size() / 3,
+                                         nn.data(), K, resolution, 1, device, texture.data(), &ts);
+        ts.knn_ms = (float)(knn_s * 1e3);
+    } else {
+        rc = pt_texture_render(index, vertices.data(), m, faces.data(), faces.size() / 3, K, radius, resolution, 1,
+                               texture.data(), &ts);
+    }
     if (rc != PT_OK) {
         std::cerr << "pt_texture_render failed: " << pt_status_string(rc) << std::endl;
         pt_index_free(index);
+        pt_sharded_free(sharded);
         return 0;
     }
     task_timer.reset();
@@ -345,10 +373,12 @@ int main(int argc, char **argv)
         // extra (not in the reference): the fused per-vertex colour / normal blend of pt_transfer
         std::vector<uint8_t> rgba(m * 4);
         std::vector<float> normal(m * 3);
-        rc = pt_transfer(index, vertices.data(), m, K, radius, nullptr, nullptr, rgba.data(), normal.data());
+        rc = sharded ? pt_sharded_transfer(sharded, vertices.data(), m, K, radius, nullptr, nullptr, rgba.data(), normal.data())
+                     : pt_transfer(index, vertices.data(), m, K, radius, nullptr, nullptr, rgba.data(), normal.data());
         if (rc != PT_OK) {
             std::cerr << "pt_transfer failed: " << pt_status_string(rc) << std::endl;
             pt_index_free(index);
+            pt_sharded_free(sharded);
             return 0;
         }
         std::ofstream out(ply_name);
@@ -373,5 +403,6 @@ int main(int argc, char **argv)
     std::cout << "Total real time: " << real_total_timer.time() << " seconds" << std::endl;
     memory_report();
     pt_index_free(index);
+    pt_sharded_free(sharded);
     return 0;
 }

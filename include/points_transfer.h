@@ -231,6 +231,45 @@ int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, 
                      int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out,
                      int *needs_exchange);
 
+/* A cloud sharded over several GPUs of one box, host side in C++ (csrc/pt_sharded.cu): x-slabs
+ * at point-count quantiles, one pt_index per slab holding the slab plus a ghost zone of width
+ * `halo`, samples routed to the slab whose x-range holds them, one host thread per slab.  Same
+ * contract as pt_knn / pt_transfer (blocking, query order, ascending (d2, index), ids are indices
+ * into the caller's `points`); results are exact for any geometry: a call that finds a ghost
+ * zone too narrow doubles `halo`, rebuilds the slabs and answers again (counted in `rebuilds`).
+ * `points` must stay valid until pt_sharded_free.  n < 2^31 points in total. */
+typedef struct pt_sharded pt_sharded;
+typedef struct pt_sharded_opts {
+    int        n_devices;  /* number of slabs, 1..64 */
+    const int *devices;    /* CUDA ordinal of every slab (may repeat); NULL => slab r on r mod device count */
+    double     halo;       /* ghost-zone width; <= 0: 4x the expected k_hint-th neighbour distance */
+    int        k_hint;     /* k the halo estimate is made for (default 20) */
+    int        coord_mode; /* PT_COORD_* */
+    int        reserved[8];
+} pt_sharded_opts;
+typedef struct pt_sharded_info {
+    int      n_slabs, rebuilds;
+    double   halo;
+    uint64_t n_points;
+    uint64_t slab_points[64], slab_ghosts[64];
+    int      slab_device[64];
+} pt_sharded_info;
+int pt_sharded_build(const void *points, size_t n, const pt_sharded_opts *opts, pt_sharded **out);
+int pt_sharded_free(pt_sharded *sharded);
+int pt_sharded_get_info(const pt_sharded *sharded, pt_sharded_info *info);
+int pt_sharded_knn(pt_sharded *sharded, const void *queries, size_t m, int k, double radius,
+                   int32_t *idx_out, double *d2_out);
+int pt_sharded_transfer(pt_sharded *sharded, const void *queries, size_t m, int k, double radius,
+                        int32_t *idx_out, double *d2_out, uint8_t *rgba_out, float *normal_out);
+
+/* pt_texture_render for neighbour lists that were computed elsewhere (e.g. pt_sharded_knn): the
+ * cloud's positions and colours are uploaded to `device` in original order, idx[n_vertices * k]
+ * (host) indexes `points`. */
+int pt_texture_render_lists(const void *points, size_t n, const void *vertices, size_t n_vertices,
+                            const int32_t *faces, size_t n_faces, const int32_t *idx, int k,
+                            int resolution, int pad, int device, uint8_t *bgra_out,
+                            pt_texture_stats *stats);
+
 /* Tuning / introspection. */
 /* Options: "knn_variant" (-1 auto [default]: grid kernel first, then scan / thread / warp for
  * the samples it hands over; 6 grid, 5 scan kernel, 2 thread kernel, 0 warp kernel),
