@@ -54,6 +54,7 @@ struct pt_sharded {
     const Rec80 *points = nullptr;    // the caller's cloud (must outlive the handle)
     size_t n = 0;
     double halo = 0.0;
+    double halo_auto = 0.0;           // the bounding-box estimate (4x the expected k-th neighbour distance)
     int coord_mode = PT_COORD_AUTO;
     int rebuilds = 0;
 };
@@ -145,7 +146,7 @@ int sharded_query(pt_sharded *S, const void *queries, size_t m, int k, double ra
         const int r = (int)(std::upper_bound(S->cuts.begin() + 1, S->cuts.end() - 1, x) - (S->cuts.begin() + 1));
         mine[r].push_back((uint32_t)i);
     }
-    for (int attempt = 0; attempt < 6; ++attempt) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
         std::vector<int> status(R, PT_OK), needs(R, 0);
         std::vector<std::thread> th;
         for (int r = 0; r < R; ++r) {
@@ -192,7 +193,7 @@ int sharded_query(pt_sharded *S, const void *queries, size_t m, int k, double ra
         }
         if (!again) return PT_OK;
         // some k-th-neighbour ball may leave a ghost zone: widen it and answer the call again
-        S->halo = S->halo > 0.0 ? 2.0 * S->halo : 1e-3;
+        S->halo = std::max(4.0 * S->halo, S->halo_auto);
         ++S->rebuilds;
         const int rc = build_slabs(S);
         if (rc != PT_OK) return rc;
@@ -242,7 +243,7 @@ int pt_sharded_build(const void *points, size_t n, const pt_sharded_opts *opts, 
     // from the bounding box (surface and volume estimate, the larger one); a call that finds it
     // too small widens it (sharded_query)
     S->halo = opts->halo;
-    if (!(S->halo > 0.0)) {
+    {
         double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (size_t i = 0; i < n; i += (n > 1000000 ? n / 1000000 : 1))
             for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], S->points[i].ver[a]); hi[a] = std::max(hi[a], S->points[i].ver[a]); }
@@ -252,8 +253,9 @@ int pt_sharded_build(const void *points, size_t n, const pt_sharded_opts *opts, 
         const double nn = n ? (double)n : 1.0;
         const double r_surface = std::sqrt(kk * std::max(e[1] * e[2], 0.0) / (M_PI * nn));
         const double r_volume = std::cbrt(3.0 * kk * std::max(e[0] * e[1] * e[2], 0.0) / (4.0 * M_PI * nn));
-        S->halo = 4.0 * std::max(r_surface, r_volume);
-        if (!(S->halo > 0.0) || !std::isfinite(S->halo)) S->halo = 1e-3;
+        S->halo_auto = 4.0 * std::max(r_surface, r_volume);
+        if (!(S->halo_auto > 0.0) || !std::isfinite(S->halo_auto)) S->halo_auto = 1e-3;
+        if (!(S->halo > 0.0)) S->halo = S->halo_auto;
     }
     const int rc = build_slabs(S);
     if (rc != PT_OK) { delete S; return rc; }
