@@ -11,7 +11,7 @@
 //             pipeline chunk -- and the results land in the caller's arrays in sample order.
 //             A step is final iff no sample's k-th-neighbour ball can leave its slab's ghost
 //             zone towards another slab (exactness argument: DESIGN.md section 6).  If some
-//             slab reports needs_exchange the halo is doubled, the slabs are rebuilt and the
+//             slab reports needs_exchange the halo is widened (x4, at least the bounding-box estimate), the slabs are rebuilt and the
 //             call is repeated, so the result is always exact; `rebuilds` counts that.
 //
 // The reference has no multi-GPU path (its query loop is src/pointsTransfer.cpp:465-479); the

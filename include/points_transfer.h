@@ -236,7 +236,7 @@ int pt_transfer_slab(pt_index *index, const void *queries, int queries_are_xyz, 
  * `halo`, samples routed to the slab whose x-range holds them, one host thread per slab.  Same
  * contract as pt_knn / pt_transfer (blocking, query order, ascending (d2, index), ids are indices
  * into the caller's `points`); results are exact for any geometry: a call that finds a ghost
- * zone too narrow doubles `halo`, rebuilds the slabs and answers again (counted in `rebuilds`).
+ * zone too narrow widens `halo`, rebuilds the slabs and answers again (counted in `rebuilds`).
  * `points` must stay valid until pt_sharded_free.  n < 2^31 points in total. */
 typedef struct pt_sharded pt_sharded;
 typedef struct pt_sharded_opts {
