@@ -50,6 +50,8 @@ int opt_grid() { return g_grid.load(); }
 int opt_grid_tma() { return g_grid_tma.load(); }
 int opt_sort_bits() { return g_sort_bits.load(); }
 size_t opt_pool_keep_bytes() { return (size_t)g_pool_keep_mb.load() << 20; }
+static std::atomic<int> g_pool_guard{0};   // debug: guard words around every device allocation (pt_build.cu)
+int opt_pool_guard() { return g_pool_guard.load(); }
 static std::atomic<int> g_host_chunks{8};   // host-buffer API: pipeline chunks per call (one stream each, up to 16)
 int opt_host_chunks() { return g_host_chunks.load(); }
 static std::atomic<int> g_queue_cap{1 << 20};   // tests: shrink the per-sample queue (exactness under spilling)
@@ -71,6 +73,7 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "grid_tma")) { g_grid_tma.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { g_sort_bits.store(value); return PT_OK; }
     if (!strcmp(name, "pool_keep_mb")) { g_pool_keep_mb.store(value < 0 ? 0 : value); return PT_OK; }
+    if (!strcmp(name, "pool_guard")) { g_pool_guard.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { g_queue_cap.store(value < 2 ? 2 : value); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { g_host_chunks.store(value < 1 ? 1 : (value > 64 ? 64 : value)); return PT_OK; }
@@ -87,6 +90,8 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "grid_tma")) { *value = g_grid_tma.load(); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { *value = g_sort_bits.load(); return PT_OK; }
     if (!strcmp(name, "pool_keep_mb")) { *value = g_pool_keep_mb.load(); return PT_OK; }
+    if (!strcmp(name, "pool_guard")) { *value = g_pool_guard.load(); return PT_OK; }
+    if (!strcmp(name, "pool_guard_hits")) { *value = guard_hits(); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { *value = g_smem_pad.load(); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { *value = g_queue_cap.load(); return PT_OK; }
     if (!strcmp(name, "host_chunks")) { *value = g_host_chunks.load(); return PT_OK; }
@@ -97,11 +102,11 @@ int get_option(const char *name, int *value)
 static int grow(void **p, size_t *cap, size_t need)
 {
     if (need <= *cap) return PT_OK;
-    if (*p) cudaFree(*p);
+    dev_free(*p);
     *p = nullptr;
     *cap = 0;
-    size_t want = need + need / 4;
-    PT_CUDA(cudaMalloc(p, want));
+    size_t want = opt_pool_guard() ? need : need + need / 4;   // guard words sit right behind the bytes in use
+    PT_TRY(dev_alloc(p, want));
     *cap = want;
     return PT_OK;
 }
@@ -122,7 +127,7 @@ static int new_index(int device, pt_index **out)
     e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     for (auto &ev : ix->ev)
         if (e == cudaSuccess) e = cudaEventCreate(&ev);
-    if (e == cudaSuccess) e = cudaMalloc(&ix->fallback_word, 16);
+    if (e == cudaSuccess && dev_alloc((void **)&ix->fallback_word, 16) != PT_OK) e = cudaErrorMemoryAllocation;
     if (e == cudaSuccess) e = cudaMemset(ix->fallback_word, 0, 16);
     int sms = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -143,13 +148,13 @@ static void destroy_index(pt_index *ix)
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (auto &c : ix->cs) if (c) cudaStreamSynchronize(c);
     // sorted points, boxes and cell tables come from the library's stream-ordered pool: back to it
-    if (ix->pts) cudaFreeAsync(ix->pts, ix->stream);
-    if (ix->boxes) cudaFreeAsync(ix->boxes, ix->stream);
-    if (ix->grid_mem) cudaFreeAsync(ix->grid_mem, ix->stream);
+    pool_free(ix->pts, ix->stream);
+    pool_free(ix->boxes, ix->stream);
+    pool_free(ix->grid_mem, ix->stream);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" (default 2 GiB) stays cached for the next build
-    cudaFree(ix->attrs); cudaFree(ix->ids); cudaFree(ix->fallback_word); cudaFree(ix->inv_perm);
-    cudaFree(ix->ws_raw); cudaFree(ix->ws_q); cudaFree(ix->ws_out);
+    dev_free(ix->attrs); dev_free(ix->ids); dev_free(ix->fallback_word); dev_free(ix->inv_perm);
+    dev_free(ix->ws_raw); dev_free(ix->ws_q); dev_free(ix->ws_out);
     for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
     for (auto &e : ix->cev) if (e) cudaEventDestroy(e);
     for (auto &ev : ix->ev) if (ev) cudaEventDestroy(ev);
@@ -232,7 +237,7 @@ int pt_index_build(const void *points, size_t n, const pt_build_opts *opts, pt_i
     int rc = ingest_points_aos(ix, points, n, mode, &xyz, &representable);
     if (rc == PT_OK && mode == PT_COORD_F32 && !representable) rc = PT_ERR_NOT_REPRESENTABLE;
     if (rc == PT_OK && opts && opts->ids && n) {
-        cudaError_t e = cudaMalloc(&ix->ids, sizeof(int32_t) * n);
+        cudaError_t e = dev_alloc((void **)&ix->ids, sizeof(int32_t) * n) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(ix->ids, opts->ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice,
                                 ix->stream);
@@ -242,7 +247,7 @@ int pt_index_build(const void *points, size_t n, const pt_build_opts *opts, pt_i
         bool f64 = mode == PT_COORD_F64 || (mode == PT_COORD_AUTO && !representable);
         rc = build_index_d3(ix, xyz, (uint32_t)n, f64);
     }
-    cudaFree(xyz);
+    dev_free(xyz);
     if (rc != PT_OK) { destroy_index(ix); return rc; }
     *out = ix;
     return PT_OK;
@@ -257,14 +262,14 @@ int pt_index_build_device(const void *pos, int coord_f64, const pt_attr *attrs,
     PT_TRY(new_index(device, &ix));
     int rc = PT_OK;
     if (n && attrs) {
-        cudaError_t e = cudaMalloc(&ix->attrs, sizeof(pt_attr) * n);
+        cudaError_t e = dev_alloc((void **)&ix->attrs, sizeof(pt_attr) * n) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(ix->attrs, attrs, sizeof(pt_attr) * n, cudaMemcpyDeviceToDevice,
                                 ix->stream);
         rc = map_cuda_error(e);
     }
     if (rc == PT_OK && n && ids) {
-        cudaError_t e = cudaMalloc(&ix->ids, sizeof(int32_t) * n);
+        cudaError_t e = dev_alloc((void **)&ix->ids, sizeof(int32_t) * n) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(ix->ids, ids, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice,
                                 ix->stream);

@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cmath>
 #include <mutex>
+#include <unordered_map>
 
 #include "pt_index.cuh"
 
@@ -480,14 +481,89 @@ static int device_pool(int dev, cudaMemPool_t *out)
     return PT_OK;
 }
 
+// Debug option "pool_guard": every device allocation of the library gets GUARD bytes of 0xA5 in
+// front and behind, checked when it is released; get_option("pool_guard_hits") counts the
+// allocations found damaged.  (The library's own bounds check: tools/sanitize.py,
+// tests/test_gpu_parity.py::test_guard_words_stay_intact.)
+constexpr size_t GUARD = 256;
+static std::mutex g_guard_mutex;
+static std::unordered_map<void *, size_t> g_guarded;   // user pointer -> user bytes
+static std::atomic<int> g_guard_hits{0};
+int guard_hits() { return g_guard_hits.load(); }
+
+static int guard_arm(void *base, size_t bytes, cudaStream_t s, void **user)
+{
+    PT_CUDA(cudaMemsetAsync(base, 0xA5, GUARD, s));
+    PT_CUDA(cudaMemsetAsync((char *)base + GUARD + bytes, 0xA5, GUARD, s));
+    *user = (char *)base + GUARD;
+    std::lock_guard<std::mutex> lock(g_guard_mutex);
+    g_guarded[*user] = bytes;
+    return PT_OK;
+}
+
+// returns the pointer to hand to cudaFree / cudaFreeAsync
+static void *guard_release(void *user, cudaStream_t s)
+{
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_guard_mutex);
+        auto it = g_guarded.find(user);
+        if (it == g_guarded.end()) return user;
+        bytes = it->second;
+        g_guarded.erase(it);
+    }
+    char *base = (char *)user - GUARD;
+    unsigned char h[2 * GUARD];
+    memset(h, 0, sizeof h);
+    cudaMemcpyAsync(h, base, GUARD, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(h + GUARD, base + GUARD + bytes, GUARD, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    int bad = 0;
+    for (size_t i = 0; i < 2 * GUARD; ++i) bad += h[i] != 0xA5;
+    if (bad) {
+        g_guard_hits.fetch_add(1);
+        fprintf(stderr, "[points_transfer] guard words damaged: %d bytes around an allocation of %zu bytes\n", bad, bytes);
+    }
+    return base;
+}
+
 int pool_alloc(void **p, size_t bytes, cudaStream_t s)
 {
     int dev = 0;
     PT_CUDA(cudaGetDevice(&dev));
     cudaMemPool_t pool;
     PT_TRY(device_pool(dev, &pool));
-    PT_CUDA(cudaMallocFromPoolAsync(p, bytes ? bytes : 16, pool, s));
-    return PT_OK;
+    if (!bytes) bytes = 16;
+    if (!opt_pool_guard()) {
+        PT_CUDA(cudaMallocFromPoolAsync(p, bytes, pool, s));
+        return PT_OK;
+    }
+    void *base = nullptr;
+    PT_CUDA(cudaMallocFromPoolAsync(&base, bytes + 2 * GUARD, pool, s));
+    return guard_arm(base, bytes, s, p);
+}
+
+void pool_free(void *p, cudaStream_t s)
+{
+    if (p) cudaFreeAsync(guard_release(p, s), s);
+}
+
+// cudaMalloc / cudaFree for the long-lived buffers of an index, with the same guard words.
+int dev_alloc(void **p, size_t bytes)
+{
+    if (!bytes) bytes = 16;
+    if (!opt_pool_guard()) {
+        PT_CUDA(cudaMalloc(p, bytes));
+        return PT_OK;
+    }
+    void *base = nullptr;
+    PT_CUDA(cudaMalloc(&base, bytes + 2 * GUARD));
+    return guard_arm(base, bytes, nullptr, p);
+}
+
+void dev_free(void *p)
+{
+    if (p) cudaFree(guard_release(p, nullptr));
 }
 
 void pool_trim(int device, size_t keep_bytes)
@@ -537,7 +613,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     }
     PT_CUDA(cudaMemcpyAsync(&h_acc, acc, sizeof h_acc, cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaStreamSynchronize(s));
-    cudaFreeAsync(acc, s);
+    pool_free(acc, s);
     if (h_acc.non_finite) return PT_ERR_NON_FINITE;
     KeyParams kp;
     double ext = 0;
@@ -571,7 +647,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     lap("keys");
     struct ArenaGuard {    // the sort arena goes back to the pool on every exit path
         char *p; cudaStream_t s;
-        ~ArenaGuard() { if (p) cudaFreeAsync(p, s); }
+        ~ArenaGuard() { pool_free(p, s); }
     } arena_guard{arena, s};
     int sort_bits = opt_sort_bits();
     sort_bits = sort_bits < 8 ? 8 : (sort_bits > 63 ? 63 : sort_bits);
@@ -633,7 +709,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     PT_CUDA(cudaStreamSynchronize(s));
     lap("boxes");
     PT_CUDA(cudaEventElapsedTime(&ix->build_ms, ix->ev[0], ix->ev[1]));
-    cudaFreeAsync(arena, s);
+    pool_free(arena, s);
     arena_guard.p = nullptr;
     cudaStreamSynchronize(s);
     pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" (default 2 GiB) of temporaries stays cached
@@ -728,12 +804,15 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
     unsigned int h_flag = 0;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    auto got = [&](int st) {
+        return ok(st == PT_OK ? cudaSuccess : st == PT_ERR_OUT_OF_MEMORY ? cudaErrorMemoryAllocation : cudaErrorUnknown);
+    };
     // chunked upload through two device staging buffers
     const size_t chunk = (size_t)1 << 22;  // 4 Mi records = 320 MiB per buffer
     const size_t cap = n < chunk ? n : chunk;
-    if (ok(cudaMalloc(&xyz, sizeof(double) * 3 * n)) && ok(cudaMalloc(&ix->attrs, sizeof(pt_attr) * n)) &&
-        ok(cudaMalloc(&flag, sizeof(unsigned int))) && ok(cudaMemsetAsync(flag, 0, sizeof(unsigned int), s)) &&
-        ok(cudaMalloc(&stage[0], sizeof(Raw80) * cap)) && ok(cudaMalloc(&stage[1], sizeof(Raw80) * cap)) &&
+    if (got(dev_alloc((void **)&xyz, sizeof(double) * 3 * n)) && got(dev_alloc((void **)&ix->attrs, sizeof(pt_attr) * n)) &&
+        got(dev_alloc((void **)&flag, sizeof(unsigned int))) && ok(cudaMemsetAsync(flag, 0, sizeof(unsigned int), s)) &&
+        got(dev_alloc((void **)&stage[0], sizeof(Raw80) * cap)) && got(dev_alloc((void **)&stage[1], sizeof(Raw80) * cap)) &&
         ok(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)) &&
         ok(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming))) {
         int b = 0;
@@ -752,11 +831,11 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
     }
     const cudaError_t es = cudaStreamSynchronize(s);      // nothing is still reading `points` after this
     if (e == cudaSuccess) e = es;
-    cudaFree(stage[0]); cudaFree(stage[1]); cudaFree(flag);
+    dev_free(stage[0]); dev_free(stage[1]); dev_free(flag);
     if (done[0]) cudaEventDestroy(done[0]);
     if (done[1]) cudaEventDestroy(done[1]);
     if (e != cudaSuccess) {
-        cudaFree(xyz);
+        dev_free(xyz);
         cudaGetLastError();
         if (verbose()) fprintf(stderr, "[points_transfer] ingest: %s\n", cudaGetErrorString(e));
         return map_cuda_error(e);

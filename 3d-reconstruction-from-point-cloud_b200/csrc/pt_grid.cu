@@ -179,13 +179,13 @@ static int build_grid_impl(pt_index *ix, const unsigned long long *keys, int low
     const int max_level = min(16, (63 - low_shift) / 3);     // levels whose cells are contiguous
 
     unsigned long long *d_hist = nullptr, h_hist[24];
-    PT_CUDA(cudaMallocAsync((void **)&d_hist, sizeof h_hist, s));
+    PT_TRY(pool_alloc((void **)&d_hist, sizeof h_hist, s));
     PT_CUDA(cudaMemsetAsync(d_hist, 0, sizeof h_hist, s));
     grid_level_hist_kernel<<<min(cdiv_u(n, GRID_BLOCK), 148u * 8u), GRID_BLOCK, 0, s>>>(keys, n, low_shift, d_hist);
     count_launch();
     PT_CUDA(cudaMemcpyAsync(h_hist, d_hist, sizeof h_hist, cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaStreamSynchronize(s));
-    cudaFreeAsync(d_hist, s);
+    pool_free(d_hist, s);
     uint64_t cells = 1;
     ix->level_cells[0] = 1;
     for (int l = 1; l <= 21; ++l) {
@@ -211,7 +211,7 @@ static int build_grid_impl(pt_index *ix, const unsigned long long *keys, int low
     }
     if (G.n_tables == 0) return PT_OK;
     GridBucket *mem = nullptr;
-    PT_CUDA(cudaMallocAsync((void **)&mem, sizeof(GridBucket) * total_buckets, s));
+    PT_TRY(pool_alloc((void **)&mem, sizeof(GridBucket) * total_buckets, s));
     ix->grid_mem = mem;
     ix->grid_bytes = sizeof(GridBucket) * total_buckets;
     PT_CUDA(cudaMemsetAsync(mem, 0xff, ix->grid_bytes, s));

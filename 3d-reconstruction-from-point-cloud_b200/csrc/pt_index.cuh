@@ -78,8 +78,13 @@ int unpack_queries_aos(const void *raw80_dev, size_t m, double *xyz_dev, cudaStr
 
 int launch_query(pt_index *ix, const QueryParams &qp, cudaStream_t s);
 // Stream-ordered allocation from the library's PRIVATE memory pool of the current device (the
-// application's default pool is never touched); release with cudaFreeAsync.
+// application's default pool is never touched); release with pool_free.  dev_alloc / dev_free:
+// cudaMalloc / cudaFree for the long-lived buffers.  Both carry guard words under "pool_guard".
 int pool_alloc(void **p, size_t bytes, cudaStream_t s);
+void pool_free(void *p, cudaStream_t s);
+int dev_alloc(void **p, size_t bytes);
+void dev_free(void *p);
+int guard_hits();
 void pool_trim(int device, size_t keep_bytes);
 int build_grid(pt_index *ix, const unsigned long long *keys, int low_shift, const double lo[3],
                double inv_cell21, double extent);
@@ -122,6 +127,7 @@ int  opt_grid();
 int  opt_grid_tma();
 int  opt_sort_bits();
 size_t opt_pool_keep_bytes();
+int  opt_pool_guard();
 int  debug_stats(unsigned long long *out16, int reset);
 
 }  // namespace pt

@@ -410,7 +410,7 @@ static int launch_chain(pt_index *ix, const QueryParams &qp, int variant, cudaSt
         e = cudaGetLastError();
         if (e != cudaSuccess) rc = map_cuda_error(e);
     }
-    cudaFreeAsync(ws, s);
+    pool_free(ws, s);
     return rc;
 }
 

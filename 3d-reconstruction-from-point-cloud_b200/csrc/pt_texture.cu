@@ -385,7 +385,7 @@ static int texture_pipeline(pt_index *ix, POS pos, uint32_t n_points, const pt_a
     } while (0);
     cudaStreamSynchronize(s);
     void *frees[] = {d_raw, d_mv, d_xyz, d_idx, d_faces, d_canvas, d_stats, d_tex, d_tmp, d_out};
-    for (void *p : frees) if (p) cudaFreeAsync(p, s);
+    for (void *p : frees) pool_free(p, s);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     cudaGetLastError();
     return rc;
@@ -397,7 +397,7 @@ static int texture_render_index(pt_index *ix, const void *vertices, size_t n_ver
                                 pt_texture_stats *st)
 {
     if (!ix->inv_perm && ix->n) {            // original index -> position in the sorted cloud, built once
-        PT_CUDA(cudaMalloc(&ix->inv_perm, sizeof(uint32_t) * (size_t)ix->n));
+        PT_TRY(dev_alloc((void **)&ix->inv_perm, sizeof(uint32_t) * (size_t)ix->n));
         tex_inverse_perm_kernel<PT><<<tcdiv(ix->n, 256), 256, 0, ix->stream>>>((const PT *)ix->pts, ix->n, ix->inv_perm);
         count_launch();
     }
@@ -450,8 +450,8 @@ extern "C" int pt_texture_render_lists(const void *points, size_t n, const void 
                               -1.0, resolution, pad, bgra_out, stats);
     }
     if (tmp.stream) cudaStreamSynchronize(tmp.stream);
-    cudaFree(xyz);
-    cudaFree(tmp.attrs);
+    dev_free(xyz);
+    dev_free(tmp.attrs);
     if (tmp.stream) cudaStreamDestroy(tmp.stream);
     cudaGetLastError();
     return rc;

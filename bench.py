@@ -541,6 +541,17 @@ def main():
     value = M / (ms_per_step * 1e-3)
     fallback = tree.fallback_counts()
     exchange = st.stats() if st is not None else None
+    if exchange is not None:
+        # whole-job totals (every rank only knows its own samples' crossings)
+        rows = exchange.get("halo_rows_per_peer") or [0] * world
+        tot = torch.tensor([exchange.get("crossing") or 0, exchange["routed_to_other_slabs"]] + list(rows),
+                           dtype=torch.int64, device=dev)
+        per_rank = [torch.empty_like(tot) for _ in range(world)]
+        dist.all_gather(per_rank, tot)
+        exchange["crossing_all_ranks"] = int(sum(int(t[0]) for t in per_rank))
+        exchange["routed_to_other_slabs_all_ranks"] = int(sum(int(t[1]) for t in per_rank))
+        if exchange.get("path") == "fast":
+            exchange["halo_rows_rank_to_peer"] = [[int(v) for v in t[2:].tolist()] for t in per_rank]
 
     # ---- exact verification of sampled results (oracle by restriction; fails the run) ------------
     verified = None

@@ -280,7 +280,9 @@ int pt_texture_render_lists(const void *points, size_t n, const void *vertices, 
  * build or a free, default 2048: a rebuild of a larger index maps fresh memory again),
  * "sort" (1 hand-written radix sort [default], 0 cub), "host_chunks" (pipeline chunks of the
  * host-buffer API, default 8), "queue_cap" (tests: per-sample traversal queue entries, at most
- * the compiled 12), "verbose", "smem_pad" (diagnosis). */
+ * the compiled 12), "verbose", "smem_pad" (diagnosis), "pool_guard" (debug: 256 guard bytes
+ * around every device allocation of the library, compared when it is released; the read-only
+ * "pool_guard_hits" counts the allocations found damaged). */
 int pt_set_option(const char *name, int value);
 int pt_get_option(const char *name, int *value);
 /* Work counters of the query kernel since the last reset (16 words; all zero unless the library

@@ -37,6 +37,7 @@ def _default_options(pkg):
     pkg.set_option("queue_cap", 1 << 20)  # the compiled capacity
     pkg.set_option("order", 1)            # Hilbert order + cell tables (the default)
     pkg.set_option("grid_tma", 1)
+    pkg.set_option("pool_guard", 0)
 
 
 # (knn_variant, order): grid / thread / warp / scan kernel x Morton, Hilbert, Hilbert + kd
@@ -473,3 +474,41 @@ def test_large_host_call_equals_oracle(k, radius, pkg, pto, torch_cuda):
             tree.transfer(qpin.numpy().view(pkg.POINT_DTYPE).reshape(-1), k, radius=radius, out=o)
             assert np.array_equal(o["idx"], ref_idx)
             _check_blend(o["rgba"], o["normal"], ref_rgba, ref_nrm)
+
+
+def test_guard_words_stay_intact(pkg, pto, torch_cuda):
+    """The library's own bounds check (compute-sanitizer is not available on the GPU pool): with
+    option "pool_guard" every device allocation is fenced by 256 bytes of 0xA5 on both sides and
+    the fences are compared when the allocation is released.  Ragged sample counts, every kernel
+    family, the texture stage and the single-process slabs: no fence may be touched, and the
+    results stay those of the oracle."""
+    pkg.set_option("pool_guard", 1)
+    before = pkg.get_option("pool_guard_hits")
+    side = 25.0
+    P = pkg.synth.cloud_host(60_001, seed=77, side=side)
+    Vall = pkg.synth.samples_host(67, side=side)        # 4 489 samples
+    kd = pto.KdTree(P)
+    for order in (1, 0, 2):
+        pkg.set_option("order", order)
+        for variant in (-1, 6, 5, 2, 0):
+            pkg.set_option("knn_variant", variant)
+            with pkg.Tree(P) as t:
+                for m, k, radius in ((1, 1, None), (31, 8, None), (33, 20, 0.4), (1000, 32, None),
+                                     (4489, 20, None), (257, 32, 0.3)):
+                    V = Vall[:m]
+                    ref_idx, ref_d2 = kd.knn(V, k, radius=-1.0 if radius is None else radius)
+                    out = t.transfer(V, k, radius=radius, want_idx=True, want_d2=True)
+                    assert np.array_equal(out["idx"], ref_idx), (order, variant, m, k)
+                    assert np.array_equal(out["d2"], ref_d2)
+    pkg.set_option("order", 1)
+    pkg.set_option("knn_variant", -1)
+    V = Vall.copy()
+    V["U"] = V["ver"][:, 0] / side * 0.9 + 0.05
+    V["V"] = V["ver"][:, 1] / side * 0.9 + 0.05
+    F = pkg.synth.grid_faces(67, 67)
+    with pkg.Tree(P) as t:
+        t.texture(V, F, k=20, resolution=300)
+    with pkg.ShardedTree(P, [0, 0, 0]) as s:
+        o = s.transfer(Vall, 20, want_idx=True)
+        assert np.array_equal(o["idx"], kd.knn(Vall, 20)[0])
+    assert pkg.get_option("pool_guard_hits") == before

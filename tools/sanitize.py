@@ -1,5 +1,7 @@
-"""Small end-to-end pass for compute-sanitizer: index build, every query kernel, the slab /
-halo kernels, the texture stage.  usage: compute-sanitizer --tool memcheck python tools/sanitize.py"""
+"""Small end-to-end pass over every kernel family (index build, every query kernel, the slab /
+halo kernels, the texture stage), written to be run under `compute-sanitizer --tool memcheck`.
+compute-sanitizer is closed on this round's GPU pool, so the pass is run plain, with the pool's
+guard words switched on instead (option "pool_guard", see pt_build.cu)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -8,6 +10,7 @@ import __graft_entry__ as ge
 
 pkg = ge.package()
 torch.cuda.set_device(0)
+pkg.set_option("pool_guard", 1)
 side = 20.0
 P = pkg.synth.cloud_host(30_000, seed=3, side=side)
 V = pkg.synth.samples_host(24, side=side)
@@ -29,3 +32,5 @@ with pkg.ShardedTree(P, [0, 0, 0]) as s:
     o2 = s.transfer(V, 20, want_idx=True)
     assert np.array_equal(o2["idx"], out["idx"])
 print("sanitize pass done:", st)
+print("pool_guard_hits", pkg.get_option("pool_guard_hits"))
+assert pkg.get_option("pool_guard_hits") == 0
