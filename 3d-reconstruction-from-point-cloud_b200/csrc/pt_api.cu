@@ -18,7 +18,7 @@ static std::atomic<int> g_order{1};   // 0 Morton, 1 Hilbert (default), 2 Hilber
 static std::atomic<int> g_grid{1};        // build the uniform-grid cell tables (pt_grid.cu)
 static std::atomic<int> g_grid_tma{1};    // stage candidate runs with cp.async.bulk (0: per-lane cp.async)
 static std::atomic<int> g_pool_keep_mb{2048};   // temporaries kept cached in the library's pool after a build / free
-static std::atomic<int> g_sort_bits{48};  // ordered key bits, from the top (cells contiguous down to level 16)
+static std::atomic<int> g_sort_bits{0};   // ordered key bits, from the top; 0 = auto (40 or 48: cells contiguous down to level 13 / 16)
 
 bool verbose()
 {

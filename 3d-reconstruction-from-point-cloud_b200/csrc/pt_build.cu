@@ -649,7 +649,11 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
         char *p; cudaStream_t s;
         ~ArenaGuard() { pool_free(p, s); }
     } arena_guard{arena, s};
+    // "sort_bits" 0 (default) = auto: 40 bits order the cells down to level 13 -- finer cells hold
+    // less than one point until a cloud has some 10^8 points (a surface fills <= 4^13 = 67 M of
+    // them), so the sixth pass would only order points inside one cell; larger clouds get 48.
     int sort_bits = opt_sort_bits();
+    if (sort_bits <= 0) sort_bits = n <= (1u << 27) ? 40 : 48;
     sort_bits = sort_bits < 8 ? 8 : (sort_bits > 63 ? 63 : sort_bits);
     const int passes = (sort_bits + 7) / 8;                      // 8-bit digits from the top of the key down
     const int first_bit = (kp.order == 2 || passes >= 8) ? 0 : 63 - 8 * passes;

@@ -2,7 +2,7 @@
 //
 // Sorts the Morton/Hilbert keys of the cloud.  8-bit digits; one
 // pass = three kernels over tiles of 2048 keys:
-//   rs_hist_kernel    per-tile digit histogram (warp-aggregated shared-memory atomics)
+//   rs_hist_kernel    per-tile digit histogram (per-warp shared-memory histograms)
 //                     -> counts[digit][tile]
 //   rs_scan_kernel    per digit, exclusive prefix over the tiles (block scan + carry), digit totals
 //   rs_scatter_kernel stable in-tile ranking with __match_any_sync (a warp walks its keys in
@@ -29,21 +29,43 @@ __global__ void __launch_bounds__(RS_THREADS)
 rs_hist_kernel(const unsigned long long *keys, uint32_t n, int shift, uint32_t num_tiles,
                uint32_t *counts)
 {
-    __shared__ uint32_t h[RS_RADIX];
-    const unsigned tid = threadIdx.x, lane = tid & 31;
-    h[tid] = 0;
+    // one private histogram per warp (plain shared-memory atomics: lanes of a warp rarely share
+    // a digit, and when the whole warp does, one lane adds for all)
+    __shared__ uint32_t h[RS_WARPS][RS_RADIX];
+    const unsigned tid = threadIdx.x, w = tid >> 5;
+#pragma unroll
+    for (int j = 0; j < RS_WARPS; ++j) h[j][tid] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * (uint32_t)RS_TILE;
-#pragma unroll 4
-    for (int it = 0; it < RS_ROUNDS; ++it) {
-        const uint32_t i = base + it * RS_THREADS + tid;
-        const bool valid = i < n;
-        const unsigned d = valid ? (unsigned)((keys[i] >> shift) & 0xffu) : 0x100u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (valid && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[d], (uint32_t)__popc(peers));
+    uint32_t *hw = h[w];
+    if (base + RS_TILE <= n) {
+        // full tile: 16-byte loads, two keys per thread and round (order is irrelevant here)
+        const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys + base);
+        ulonglong2 v[RS_ROUNDS / 2];
+#pragma unroll
+        for (int it = 0; it < RS_ROUNDS / 2; ++it) v[it] = __ldg(k2 + it * RS_THREADS + tid);
+#pragma unroll
+        for (int it = 0; it < RS_ROUNDS / 2; ++it) {
+            const unsigned d0 = (unsigned)(v[it].x >> shift) & 0xffu, d1 = (unsigned)(v[it].y >> shift) & 0xffu;
+            const unsigned first = __shfl_sync(0xffffffffu, d0, 0);
+            if (__all_sync(0xffffffffu, d0 == first && d1 == first)) {
+                if ((tid & 31) == 0) atomicAdd(&hw[first], 64u);
+            } else {
+                atomicAdd(&hw[d0], 1u);
+                atomicAdd(&hw[d1], 1u);
+            }
+        }
+    } else {
+        for (int it = 0; it < RS_ROUNDS; ++it) {
+            const uint32_t i = base + it * RS_THREADS + tid;
+            if (i < n) atomicAdd(&hw[(unsigned)(keys[i] >> shift) & 0xffu], 1u);
+        }
     }
     __syncthreads();
-    counts[(size_t)tid * num_tiles + blockIdx.x] = h[tid];
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < RS_WARPS; ++j) c += h[j][tid];
+    counts[(size_t)tid * num_tiles + blockIdx.x] = c;
 }
 
 // One block per digit: exclusive prefix of counts[digit][0..num_tiles) in place, total out.

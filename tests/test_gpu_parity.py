@@ -38,6 +38,7 @@ def _default_options(pkg):
     pkg.set_option("order", 1)            # Hilbert order + cell tables (the default)
     pkg.set_option("grid_tma", 1)
     pkg.set_option("pool_guard", 0)
+    pkg.set_option("sort_bits", 0)
 
 
 # (knn_variant, order): grid / thread / warp / scan kernel x Morton, Hilbert, Hilbert + kd
@@ -512,3 +513,21 @@ def test_guard_words_stay_intact(pkg, pto, torch_cuda):
         o = s.transfer(Vall, 20, want_idx=True)
         assert np.array_equal(o["idx"], kd.knn(Vall, 20)[0])
     assert pkg.get_option("pool_guard_hits") == before
+
+
+@pytest.mark.parametrize("bits", [16, 24, 40, 48, 63])
+def test_any_number_of_ordered_key_bits_is_exact(bits, pkg, pto, torch_cuda):
+    """The radix sort orders only the top `sort_bits` key bits (auto: 40 or 48).  Cell tables
+    are built down to the finest level those bits keep contiguous, so every setting -- also one
+    that leaves only 5 levels -- answers exactly, on every kernel."""
+    pkg.set_option("sort_bits", bits)
+    P = pkg.synth.cloud_host(150_000, seed=91, side=60.0)
+    V = pkg.synth.samples_host(50, side=60.0)
+    k = 20
+    ref_idx, ref_d2 = pto.KdTree(P).knn(V, k)
+    for variant in (-1, 6, 5):
+        pkg.set_option("knn_variant", variant)
+        with pkg.Tree(P) as t:
+            out = t.transfer(V, k, want_idx=True, want_d2=True)
+        assert np.array_equal(out["idx"], ref_idx), (bits, variant)
+        assert np.array_equal(out["d2"], ref_d2)
