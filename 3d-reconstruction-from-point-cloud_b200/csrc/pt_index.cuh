@@ -125,6 +125,7 @@ int  opt_smem_pad();
 int  opt_queue_cap();
 int  opt_grid();
 int  opt_grid_tma();
+int  opt_grid_pair();
 int  opt_sort_bits();
 size_t opt_pool_keep_bytes();
 int  opt_pool_guard();

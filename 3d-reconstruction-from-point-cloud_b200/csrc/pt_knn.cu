@@ -13,6 +13,7 @@
 //     first DFS, top-k as a sorted list distributed one entry per lane.  Most instructions per
 //     sample but the shortest latency and no per-sample state limits: it answers small launches
 //     and re-runs the samples the other two hand over (exact fallback).
+#include <type_traits>
 #include "pt_index.cuh"
 
 namespace pt {

@@ -29,6 +29,9 @@
 
 namespace pt {
 
+#ifndef PT_PAIR_OPT
+#define PT_PAIR_OPT 6
+#endif
 constexpr int GRID_CAP = 256;         // staged candidates per sample (8-bit slot numbers)
 #ifndef PT_GRID_WARPS
 #define PT_GRID_WARPS 4
@@ -135,11 +138,19 @@ __device__ __forceinline__ void grid_lookup(const GridBucket *buckets, uint32_t 
             const unsigned rank = (a.y >> (3 * oct)) & 7u;
             const uint32_t total = c.x & 0xffffu;
             if (total == 0xffffu) { cnt = 0xffffffffu; return; }
+            const unsigned r1 = rank + 1;
+#if PT_PAIR_OPT & 8
+            // 16-bit field r of the 128-bit cum[]: pick the 64-bit half, then two bytes of it
+            const uint32_t bx = rank < 4 ? c.x : c.z, by = rank < 4 ? c.y : c.w;
+            const uint32_t ex = r1 < 4 ? c.x : c.z, ey = r1 < 4 ? c.y : c.w;
+            const uint32_t beg = rank ? (__byte_perm(bx, by, 0x4410u + 0x22u * (rank & 3u)) & 0xffffu) : 0u;
+            const uint32_t end = rank < 7 ? (__byte_perm(ex, ey, 0x4410u + 0x22u * (r1 & 3u)) & 0xffffu) : total;
+#else
             const unsigned long long lo = (unsigned long long)c.x | ((unsigned long long)c.y << 32);
             const unsigned long long hi = (unsigned long long)c.z | ((unsigned long long)c.w << 32);
-            const unsigned r1 = rank + 1;
             const uint32_t beg = rank ? (uint32_t)((rank < 4 ? lo >> (16 * rank) : hi >> (16 * (rank - 4))) & 0xffffu) : 0u;
             const uint32_t end = rank < 7 ? (uint32_t)((r1 < 4 ? lo >> (16 * r1) : hi >> (16 * (r1 - 4))) & 0xffffu) : total;
+#endif
             start = a.x + beg;
             cnt = end - beg;
             return;
@@ -165,6 +176,18 @@ template <> __device__ __forceinline__ void gkey_sort<8>(uint32_t (&h)[8])   // 
     PT_GCAS(0, 4) PT_GCAS(1, 5) PT_GCAS(2, 6) PT_GCAS(3, 7)
     PT_GCAS(2, 4) PT_GCAS(3, 5)
     PT_GCAS(1, 2) PT_GCAS(3, 4) PT_GCAS(5, 6)
+}
+template <> __device__ __forceinline__ void gkey_sort<12>(uint32_t (&h)[12])   // 39 exchanges, depth 9
+{
+    PT_GCAS(0, 8) PT_GCAS(1, 7) PT_GCAS(2, 6) PT_GCAS(3, 11) PT_GCAS(4, 10) PT_GCAS(5, 9)
+    PT_GCAS(0, 1) PT_GCAS(2, 5) PT_GCAS(3, 4) PT_GCAS(6, 9) PT_GCAS(7, 8) PT_GCAS(10, 11)
+    PT_GCAS(0, 2) PT_GCAS(1, 6) PT_GCAS(5, 10) PT_GCAS(9, 11)
+    PT_GCAS(0, 3) PT_GCAS(1, 2) PT_GCAS(4, 6) PT_GCAS(5, 7) PT_GCAS(8, 11) PT_GCAS(9, 10)
+    PT_GCAS(1, 4) PT_GCAS(3, 5) PT_GCAS(6, 8) PT_GCAS(7, 10)
+    PT_GCAS(1, 3) PT_GCAS(2, 5) PT_GCAS(6, 9) PT_GCAS(8, 10)
+    PT_GCAS(2, 3) PT_GCAS(4, 5) PT_GCAS(6, 7) PT_GCAS(8, 9)
+    PT_GCAS(4, 6) PT_GCAS(5, 7)
+    PT_GCAS(3, 4) PT_GCAS(5, 6) PT_GCAS(7, 8)
 }
 #undef PT_GCAS
 
@@ -547,9 +570,390 @@ knn_grid_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
     }
 }
 
+
+// ---- two samples per warp (k <= 16, float4 records, first attempt with rc = 1) ------------------
+// Most of a sample's instructions are warp-uniform bookkeeping that 32 lanes execute for one
+// sample (set-up, scan, selection rounds, blend epilogue: profiles/README.md).  Here a warp
+// answers samples 2p and 2p + 1 at once, 16 lanes each: sub-lane c looks up cells c and c + 16 of
+// the 3^3 block, every half stages its runs into its own PAIR_CAP slots (one mbarrier for
+// both), lanes take the staged candidates 16 apart, the selection rounds reduce over 16-lane
+// segments, and sub-lane r ends up with the r-th neighbour.  A half that cannot be proven final
+// by this first attempt (list not full, more than PAIR_CAP candidates, dense bucket, k-th
+// distance beyond the block) is redone by the whole warp through grid_sample -- the complete
+// attempt schedule, staging rounds and the hand-over to the box-pyramid kernels.
+#ifndef PT_PAIR_CAP
+#define PT_PAIR_CAP 192
+#endif
+constexpr int PAIR_CAP = PT_PAIR_CAP;  // staged candidates per sample (128 or 192); slot numbers stay 8-bit
+
+__device__ __forceinline__ uint32_t seg16_min(uint32_t v)
+{
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, 8));
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return v;
+}
+
+// grid_select for a half-warp: slots sl, sl + 16, ... below `total` (0: the half sits out).
+// `amb` is per lane; the caller combines it over the half.
+template <int C>
+__device__ __forceinline__ void pair_select(const PointF *cand, uint32_t total, double qx, double qy,
+                                            double qz, double r2, int k, unsigned sl, bool upper,
+                                            uint32_t &mine, bool &amb)
+{
+    uint32_t h[C];
+#pragma unroll
+    for (int u = 0; u < C; ++u) {
+        const uint32_t j = sl + 16u * u;
+        uint32_t key = GKEY_NONE;
+        if (j < total) {
+            double px, py, pz;
+            int pidx;
+            GridRec<PointF>::load(cand, j, px, py, pz, pidx);
+            const double d = dist2_exact(qx, qy, qz, px, py, pz);
+            if (d <= r2) key = (__float_as_uint(__double2float_rd(d)) & ~0xffu) | j;
+        }
+        h[u] = key;
+    }
+    gkey_sort<C>(h);
+    mine = GKEY_NONE;
+    uint32_t m = GKEY_NONE;
+#pragma unroll 2
+    for (int r = 0; r <= k; ++r) {
+#if PT_PAIR_OPT & 2
+        // two independent full-warp REDUX.MIN, each over one half's heads
+        const uint32_t mA = __reduce_min_sync(0xffffffffu, upper ? GKEY_NONE : h[0]);
+        const uint32_t mB = __reduce_min_sync(0xffffffffu, upper ? h[0] : GKEY_NONE);
+        m = upper ? mB : mA;
+#else
+        m = seg16_min(h[0]);
+#endif
+        if ((unsigned)r == sl) mine = m;
+        if ((m & 15u) == sl) {             // the owner pops its head
+#pragma unroll
+            for (int u = 0; u + 1 < C; ++u) h[u] = h[u + 1];
+            h[C - 1] = GKEY_NONE;
+        }
+    }
+    uint32_t nxt = __shfl_down_sync(0xffffffffu, mine, 1);
+    if (sl == 15u) nxt = m;                     // k == 16: the 17th key is only in m
+    amb = sl < (unsigned)k && mine != GKEY_NONE && (mine >> 8) == (nxt >> 8);
+    if (sl >= (unsigned)k) mine = GKEY_NONE;
+}
+
+// grid_select_exact for the halves with act == true (the other half keeps its `mine`).
+__device__ __forceinline__ void pair_select_exact(const PointF *cand, bool act, uint32_t total, double qx,
+                                                  double qy, double qz, double r2, int k, unsigned lane,
+                                                  uint32_t &mine)
+{
+    const unsigned sl = lane & 15u, hbase = lane & 16u;
+    uint32_t taken = 0;
+    if (act) mine = GKEY_NONE;
+#pragma unroll 1
+    for (int r = 0; r < k; ++r) {
+        double bd = INFINITY;
+        int bi = IDX_NONE, bu = -1;
+        if (act) {
+#pragma unroll 1
+            for (int u = 0; sl + 16u * u < total; ++u) {
+                if ((taken >> u) & 1u) continue;
+                double px, py, pz;
+                int pidx;
+                GridRec<PointF>::load(cand, sl + 16u * u, px, py, pz, pidx);
+                const double d = dist2_exact(qx, qy, qz, px, py, pz);
+                if (d <= r2 && (bu < 0 || key_less(d, pidx, bd, bi))) { bd = d; bi = pidx; bu = u; }
+            }
+        }
+        bool in = bu >= 0;
+        if (!__any_sync(0xffffffffu, in)) break;
+        const uint32_t hi = in ? (uint32_t)__double2hiint(bd) : 0xffffffffu;
+        const uint32_t mh = seg16_min(hi);
+        in = in && hi == mh;
+        const uint32_t lo = in ? (uint32_t)__double2loint(bd) : 0xffffffffu;
+        const uint32_t ml = seg16_min(lo);
+        in = in && lo == ml;
+        const uint32_t ii = in ? (uint32_t)bi : 0xffffffffu;
+        const uint32_t mi = seg16_min(ii);
+        in = in && ii == mi;
+        const uint32_t seg = (__ballot_sync(0xffffffffu, in) >> hbase) & 0xffffu;
+        const int w = (int)hbase + (seg ? __ffs(seg) - 1 : 0);
+        const uint32_t jw = __shfl_sync(0xffffffffu, sl + 16u * (uint32_t)(bu < 0 ? 0 : bu), w);
+        if (seg && lane == (unsigned)w) taken |= 1u << bu;
+        if (seg && act && (unsigned)r == sl) mine = jw;
+    }
+}
+
+// Outputs of both halves at once: sub-lane r holds the r-th neighbour of sample s (em: this
+// half's answer is final).  Same arithmetic, in the same order, as the epilogue of grid_sample.
+__device__ __forceinline__ void pair_emit(const QueryParams &P, uint32_t s, bool em, uint32_t mine, double d,
+                                          int li, unsigned lane, PointF *wcand)
+{
+    const unsigned sl = lane & 15u, hbase = lane & 16u;
+    const int k = P.k;
+    const bool has = em && mine != GKEY_NONE;
+    const int gid = has ? (P.ids ? __ldg(P.ids + li) : li) : -1;
+    const bool want_blend = P.rgba_out || P.normal_out;
+    AttrRaw at{0.f, 0.f, 0.f, 0u};
+    if (has && (want_blend || P.cand_out) && P.attrs) at = load_attr(P.attrs + li);
+    if (em && sl < (unsigned)k) {
+        const size_t o = (size_t)s * k + sl;
+        if (P.idx_out) P.idx_out[o] = gid;
+        if (P.d2_out) P.d2_out[o] = d;
+        if (P.cand_out) store_cand(P.cand_out + o, d, gid, at);
+    }
+    if (!want_blend) return;
+    uint8_t *ro = P.rgba_out ? P.rgba_out + 4 * (size_t)s : nullptr;
+    float *no = P.normal_out ? P.normal_out + 3 * (size_t)s : nullptr;
+    const int cnt = __popc((__ballot_sync(0xffffffffu, has) >> hbase) & 0xffffu);
+    if (em && cnt == 0 && sl == 0u) store_empty_blend(ro, no);
+    const bool bl = em && cnt > 0;
+    if (!__any_sync(0xffffffffu, bl)) return;
+    const int mode = __shfl_sync(0xffffffffu, d, (int)hbase) == 0.0 ? 1 : 0;
+    const double w = has ? (mode ? (d == 0.0 ? 1.0 : 0.0) : __ddiv_rn(1.0, d)) : 0.0;
+    double *tile = reinterpret_cast<double *>(wcand);
+    __syncwarp();                               // every lane has read its winner's record
+    tile[0 * 32 + lane] = w;
+    tile[1 * 32 + lane] = __dmul_rn(w, (double)(at.rgba & 0xffu));
+    tile[2 * 32 + lane] = __dmul_rn(w, (double)((at.rgba >> 8) & 0xffu));
+    tile[3 * 32 + lane] = __dmul_rn(w, (double)((at.rgba >> 16) & 0xffu));
+    tile[4 * 32 + lane] = __dmul_rn(w, (double)at.nx);
+    tile[5 * 32 + lane] = __dmul_rn(w, (double)at.ny);
+    tile[6 * 32 + lane] = __dmul_rn(w, (double)at.nz);
+    __syncwarp();
+    double acc = 0.0;
+    if (bl && sl < 7u) {
+        const double *row = tile + sl * 32u + hbase;
+        int j = 0;
+#pragma unroll 1
+        for (; j + 4 <= cnt; j += 4) {
+            acc = __dadd_rn(acc, row[j]);
+            acc = __dadd_rn(acc, row[j + 1]);
+            acc = __dadd_rn(acc, row[j + 2]);
+            acc = __dadd_rn(acc, row[j + 3]);
+        }
+#pragma unroll 1
+        for (; j < cnt; ++j) acc = __dadd_rn(acc, row[j]);
+    }
+    double s0 = __shfl_sync(0xffffffffu, acc, (int)hbase);
+    if (bl && !(s0 > 0.0 && s0 < INFINITY)) {   // overflowed weights: nearest neighbour only
+        const uint32_t c0 = __shfl_sync(0xffffffffu, at.rgba, (int)hbase);   // (all lanes of the half are here)
+        const float n0x = __shfl_sync(0xffffffffu, at.nx, (int)hbase), n0y = __shfl_sync(0xffffffffu, at.ny, (int)hbase),
+                    n0z = __shfl_sync(0xffffffffu, at.nz, (int)hbase);
+        const double v[7] = {1.0, (double)(c0 & 0xffu), (double)((c0 >> 8) & 0xffu), (double)((c0 >> 16) & 0xffu),
+                             (double)n0x, (double)n0y, (double)n0z};
+        acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 7; ++a) if (sl == (unsigned)a) acc = v[a];
+        s0 = 1.0;
+    }
+    const double s4 = __shfl_sync(0xffffffffu, acc, (int)hbase + 4), s5 = __shfl_sync(0xffffffffu, acc, (int)hbase + 5),
+                 s6 = __shfl_sync(0xffffffffu, acc, (int)hbase + 6);
+    const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(s4, s4), __dmul_rn(s5, s5)), __dmul_rn(s6, s6)));
+    const double den = sl < 4u ? s0 : len;
+    const double quo = __ddiv_rn(acc, den);
+    const int ci = min(max(__double2int_rz(quo), 0), 255);
+    const int cr = __shfl_sync(0xffffffffu, ci, (int)hbase + 1), cg = __shfl_sync(0xffffffffu, ci, (int)hbase + 2),
+              cb = __shfl_sync(0xffffffffu, ci, (int)hbase + 3);
+    if (bl && sl == 0u && ro) *reinterpret_cast<uchar4 *>(ro) = make_uchar4((unsigned char)cr, (unsigned char)cg, (unsigned char)cb, 255);
+    if (bl && sl >= 4u && sl < 7u && no)
+        no[sl - 4u] = (len > 0.0 && len < INFINITY) ? __double2float_rn(quo) : 0.0f;
+}
+
+#ifndef PT_PAIR_MIN_BLOCKS
+#define PT_PAIR_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(GRID_WARPS * 32, PT_PAIR_MIN_BLOCKS)
+knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
+{
+    extern __shared__ __align__(128) unsigned char g_smem[];
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned sl = lane & 15u, hbase = lane & 16u;
+    PointF *wcand = reinterpret_cast<PointF *>(g_smem) + (size_t)wib * (2 * PAIR_CAP);
+    PointF *cand = wcand + (hbase ? PAIR_CAP : 0);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(g_smem + sizeof(PointF) * 2 * PAIR_CAP * GRID_WARPS);
+    const uint32_t bar = smem_u32(bars + wib);
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    uint32_t phase = 0;
+    const int k = P.k;
+    const GridParams &G = P.grid;
+    const uint32_t n_warps = gridDim.x * GRID_WARPS, n_pairs = (P.m + 1u) >> 1;
+    const PointF *pts = reinterpret_cast<const PointF *>(P.pts);
+    uint32_t p = blockIdx.x * GRID_WARPS + wib;
+    if (p >= n_pairs) return;
+#if PT_PAIR_OPT & 4
+    while (p < n_pairs) {
+        // a pair whose second sample does not exist answers the first one twice and emits it once
+        const bool valid = 2u * p + (lane >> 4) < P.m;
+        const uint32_t s = min(2u * p + (lane >> 4), P.m - 1u);
+        const double qx = __ldg(P.queries + 3 * (size_t)s), qy = __ldg(P.queries + 3 * (size_t)s + 1),
+                     qz = __ldg(P.queries + 3 * (size_t)s + 2);
+        if (lane == 0 && p + n_warps < n_pairs)      // the next pair's coordinates: towards L2 meanwhile
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.queries + 6 * (size_t)(p + n_warps)));
+#else
+    // a pair whose second sample does not exist answers the first one twice and emits it once
+    uint32_t s = min(2u * p + (lane >> 4), P.m - 1u);
+    double qx = __ldg(P.queries + 3 * (size_t)s), qy = __ldg(P.queries + 3 * (size_t)s + 1),
+           qz = __ldg(P.queries + 3 * (size_t)s + 2);
+    while (p < n_pairs) {
+        const bool valid = 2u * p + (lane >> 4) < P.m;
+        const uint32_t pn = p + n_warps;
+        uint32_t sn = s;
+        double nx = 0.0, ny = 0.0, nz = 0.0;
+        if (pn < n_pairs) {
+            sn = min(2u * pn + (lane >> 4), P.m - 1u);
+            nx = __ldg(P.queries + 3 * (size_t)sn);
+            ny = __ldg(P.queries + 3 * (size_t)sn + 1);
+            nz = __ldg(P.queries + 3 * (size_t)sn + 2);
+        }
+#endif
+        const double r2 = P.r2_per_query ? __ldg(P.r2_per_query + s) : P.r2;
+        // ---- the sample's cell and its distance to the faces of the 3^3 block (see grid_sample) ---
+        const GridTable &T = G.tab[G.att_tab[0]];
+        const int sh = 21 - T.level;
+        const uint32_t ncell = 1u << T.level;
+        const float S = (float)(1u << sh), above = 2.0f * S;
+        const double qv[3] = {qx, qy, qz};
+        uint32_t c[3];
+        float gl = INFINITY;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            const double t = (qv[ax] - G.lo[ax]) * G.inv_cell21;
+            const uint32_t c21 = min(__double2uint_rz(t), 2097151u);
+            c[ax] = c21 >> sh;
+            const double f = t - (double)(c[ax] << sh);
+            const float dl = __fadd_rd(__double2float_rd(f), S);
+            const float du = __fsub_rd(above, __double2float_ru(f));
+            gl = fminf(gl, c[ax] > 1u ? dl : INFINITY);
+            gl = fminf(gl, c[ax] + 2u < ncell ? du : INFINITY);
+        }
+        // (|x| + |y| + |z| bounds the largest coordinate from above)
+        const double slack = G.slack + 1.8e-15 * (fabs(qx) + fabs(qy) + fabs(qz));
+        const double g = (double)gl * G.cell21 - slack;
+        const double g2 = g > 0.0 ? __dmul_rd(g, g) : 0.0;
+        // ---- look-ups: sub-lane c takes cells c and c + 16 ---------------------------------------
+        uint32_t st0 = 0, ct0 = 0, st1 = 0, ct1 = 0;
+        bool dense = false;
+        {
+            const uint32_t n1 = sl + 16u;
+            const uint32_t x0 = c[0] + sl % 3u - 1u, y0 = c[1] + (sl / 3u) % 3u - 1u, z0 = c[2] + sl / 9u - 1u;
+            const uint32_t x1 = c[0] + n1 % 3u - 1u, y1 = c[1] + (n1 / 3u) % 3u - 1u, z1 = c[2] + n1 / 9u - 1u;
+            const bool ok0 = valid && x0 < ncell && y0 < ncell && z0 < ncell;
+            const bool ok1 = valid && n1 < 27u && x1 < ncell && y1 < ncell && z1 < ncell;
+            // (issuing both first probes before examining either was measured: the extra live
+            // registers cost more than the second round trip)
+            if (ok0) grid_lookup(T.buckets, T.cap, x0, y0, z0, st0, ct0);
+            if (ok1) grid_lookup(T.buckets, T.cap, x1, y1, z1, st1, ct1);
+            if (ct0 == 0xffffffffu) { dense = true; ct0 = 0; }
+            if (ct1 == 0xffffffffu) { dense = true; ct1 = 0; }
+        }
+        const uint32_t mysum = ct0 + ct1;
+        uint32_t incl = mysum;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (sl >= (unsigned)o) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, (int)(hbase | 15u));
+        const bool dense_h = ((__ballot_sync(0xffffffffu, dense) >> hbase) & 0xffffu) != 0u;
+        const bool go = valid && !dense_h && total <= (uint32_t)PAIR_CAP && (total >= (uint32_t)k || r2 <= g2);
+        const uint32_t tot = go ? total : 0u;
+        const uint32_t tA = __shfl_sync(0xffffffffu, tot, 0), tB = __shfl_sync(0xffffffffu, tot, 16);
+#ifdef PT_STATS
+        if (sl == 0 && valid) { atomicAdd(&g_stats[12], 1ull); atomicAdd(&g_stats[13], (unsigned long long)tot); }
+#endif
+        // ---- stage both halves' runs; one mbarrier ------------------------------------------------
+        if (tA + tB > 0u) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect(bar, (tA + tB) * (uint32_t)sizeof(PointF));
+            __syncwarp();
+            const uint32_t excl = incl - mysum;
+            if (go && ct0) bulk_g2s(smem_u32(cand + excl), pts + st0, ct0 * (uint32_t)sizeof(PointF), bar);
+            if (go && ct1) bulk_g2s(smem_u32(cand + excl + ct0), pts + st1, ct1 * (uint32_t)sizeof(PointF), bar);
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
+        // ---- select --------------------------------------------------------------------------------
+        uint32_t mine = GKEY_NONE;
+        bool amb = false;
+        const uint32_t tmax = max(tA, tB);
+        if (tmax <= 32u) pair_select<2>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
+        else if (tmax <= 64u) pair_select<4>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
+#if PT_PAIR_CAP > 128
+        else if (tmax <= 128u) pair_select<8>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
+        else pair_select<12>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
+#else
+        else pair_select<8>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
+#endif
+        const uint32_t amb_all = __ballot_sync(0xffffffffu, amb);
+        if (amb_all) {
+            const bool act = ((amb_all >> hbase) & 0xffffu) != 0u;
+#ifdef PT_STATS
+            if (sl == 0 && act) atomicAdd(&g_stats[14], 1ull);
+#endif
+            pair_select_exact(cand, act, tot, qx, qy, qz, r2, k, lane, mine);
+        }
+        double d = INFINITY;
+        int li = IDX_NONE;
+        if (mine != GKEY_NONE) {
+            double px, py, pz;
+            GridRec<PointF>::load(cand, mine & 0xffu, px, py, pz, li);
+            d = dist2_exact(qx, qy, qz, px, py, pz);
+        }
+        const double kth = __shfl_sync(0xffffffffu, d, (int)hbase + k - 1);   // +inf while the list is short
+        const bool done = go && fmin(kth, r2) <= g2;
+        pair_emit(P, s, done, mine, d, li, lane, wcand);
+        // ---- halves this attempt could not finish: the whole warp, the whole schedule ----------------
+        const uint32_t redo = __ballot_sync(0xffffffffu, valid && !done);
+#if PT_PAIR_OPT & 16
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+            if (((redo >> (16 * hh)) & 1u) == 0u) continue;
+            const double fx = __shfl_sync(0xffffffffu, qx, 16 * hh), fy = __shfl_sync(0xffffffffu, qy, 16 * hh),
+                         fz = __shfl_sync(0xffffffffu, qz, 16 * hh);
+            grid_sample<PointF, true>(P, 2u * p + (uint32_t)hh, fx, fy, fz, lane, wcand, bar, phase, ovf_count, ovf_list);
+        }
+#else
+        if (redo & 1u) {
+            const double fx = __shfl_sync(0xffffffffu, qx, 0), fy = __shfl_sync(0xffffffffu, qy, 0),
+                         fz = __shfl_sync(0xffffffffu, qz, 0);
+            grid_sample<PointF, true>(P, 2u * p, fx, fy, fz, lane, wcand, bar, phase, ovf_count, ovf_list);
+        }
+        if (redo & 0x10000u) {
+            const double fx = __shfl_sync(0xffffffffu, qx, 16), fy = __shfl_sync(0xffffffffu, qy, 16),
+                         fz = __shfl_sync(0xffffffffu, qz, 16);
+            grid_sample<PointF, true>(P, 2u * p + 1u, fx, fy, fz, lane, wcand, bar, phase, ovf_count, ovf_list);
+        }
+#endif
+#if PT_PAIR_OPT & 4
+        p += n_warps;
+#else
+        p = pn; s = sn; qx = nx; qy = ny; qz = nz;
+#endif
+    }
+}
+
 static inline size_t grid_kernel_smem(size_t rec_bytes)
 {
     return rec_bytes * GRID_CAP * GRID_WARPS + 8 * GRID_WARPS;
+}
+
+static int launch_grid_pair(const QueryParams &qp, int sm_count, uint32_t *count, uint32_t *list, cudaStream_t s)
+{
+    const size_t smem = sizeof(PointF) * 2 * PAIR_CAP * GRID_WARPS + 8 * GRID_WARPS;
+    if (smem > 48 * 1024)
+        PT_CUDA(cudaFuncSetAttribute(knn_grid_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, knn_grid_pair_kernel, GRID_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned want = ((qp.m + 1u) / 2u + GRID_WARPS - 1) / GRID_WARPS;
+    const unsigned resident = (unsigned)(sm_count * per_sm);
+    knn_grid_pair_kernel<<<want < resident ? want : resident, GRID_WARPS * 32, smem, s>>>(qp, count, list);
+    count_launch();
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
 }
 
 template <typename PT>
@@ -557,6 +961,10 @@ static int launch_grid(const QueryParams &qp, int sm_count, uint32_t *count, uin
 {
     const size_t smem = grid_kernel_smem(sizeof(PT));
     const bool tma = opt_grid_tma() != 0;
+    // two samples per warp when the lists fit a half-warp and the first attempt is a 3^3 block
+    if (std::is_same<PT, PointF>::value && tma && opt_grid_pair() != 0 && qp.k <= 16 && qp.grid.n_attempts > 0 &&
+        qp.grid.att_rc[0] == 1)
+        return launch_grid_pair(qp, sm_count, count, list, s);
     auto kern = tma ? knn_grid_kernel<PT, true> : knn_grid_kernel<PT, false>;
     if (smem > 48 * 1024)
         PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

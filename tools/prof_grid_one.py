@@ -20,6 +20,8 @@ q = pkg.synth.samples_device(g, g, center=w.center)
 m = q.shape[0]
 tree = pkg.DeviceTree(pos, attrs)
 pkg.set_option("verbose", 0)
+if os.environ.get("PT_PAIR"):
+    pkg.set_option("grid_pair", int(os.environ["PT_PAIR"]))
 if os.environ.get("PT_VARIANT"):
     pkg.set_option("knn_variant", int(os.environ["PT_VARIANT"]))
 idx = torch.empty((m, k), dtype=torch.int32, device="cuda")
