@@ -50,6 +50,8 @@ int opt_grid() { return g_grid.load(); }
 int opt_grid_tma() { return g_grid_tma.load(); }
 static std::atomic<int> g_grid_pair{1};   // grid kernel: two samples per warp when k <= 16
 int opt_grid_pair() { return g_grid_pair.load(); }
+static std::atomic<int> g_grid_pair_used{0};   // introspection: did the last grid launch run two samples per warp
+void note_grid_pair_used(int used) { g_grid_pair_used.store(used); }
 int opt_sort_bits() { return g_sort_bits.load(); }
 size_t opt_pool_keep_bytes() { return (size_t)g_pool_keep_mb.load() << 20; }
 static std::atomic<int> g_pool_guard{0};   // debug: guard words around every device allocation (pt_build.cu)
@@ -73,7 +75,7 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "sort")) { g_sort.store(value); return PT_OK; }
     if (!strcmp(name, "grid")) { g_grid.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "grid_tma")) { g_grid_tma.store(value ? 1 : 0); return PT_OK; }
-    if (!strcmp(name, "grid_pair")) { g_grid_pair.store(value ? 1 : 0); return PT_OK; }
+    if (!strcmp(name, "grid_pair")) { g_grid_pair.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { g_sort_bits.store(value); return PT_OK; }
     if (!strcmp(name, "pool_keep_mb")) { g_pool_keep_mb.store(value < 0 ? 0 : value); return PT_OK; }
     if (!strcmp(name, "pool_guard")) { g_pool_guard.store(value ? 1 : 0); return PT_OK; }
@@ -92,6 +94,7 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "grid")) { *value = g_grid.load(); return PT_OK; }
     if (!strcmp(name, "grid_tma")) { *value = g_grid_tma.load(); return PT_OK; }
     if (!strcmp(name, "grid_pair")) { *value = g_grid_pair.load(); return PT_OK; }
+    if (!strcmp(name, "grid_pair_used")) { *value = g_grid_pair_used.load(); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { *value = g_sort_bits.load(); return PT_OK; }
     if (!strcmp(name, "pool_keep_mb")) { *value = g_pool_keep_mb.load(); return PT_OK; }
     if (!strcmp(name, "pool_guard")) { *value = g_pool_guard.load(); return PT_OK; }

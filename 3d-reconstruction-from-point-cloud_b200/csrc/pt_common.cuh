@@ -98,6 +98,7 @@ struct GridParams {
     // is not provably final
     int       n_attempts;
     unsigned char att_tab[GRID_MAX_ATTEMPTS], att_rc[GRID_MAX_ATTEMPTS];
+    float     expect_cand;     // candidates the first attempt is expected to stage per sample (host estimate)
 };
 
 struct QueryParams {

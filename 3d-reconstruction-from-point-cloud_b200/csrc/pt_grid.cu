@@ -273,10 +273,13 @@ int grid_plan(const pt_index *ix, int k, double r2, GridParams &gp)
         for (int rc = 1; rc <= 2; ++rc) {
             if ((double)rc < 1.2 * rk_cells) continue;
             const double cost = pow(2.0 * rc + 1.0, d) * occ + 8.0 * (rc == 1 ? 8 : 27);
-            if (cost < best_cost) { best_cost = cost; best_t = t; best_rc = rc; }
+            if (cost < best_cost) {
+                best_cost = cost; best_t = t; best_rc = rc;
+                gp.expect_cand = (float)(pow(2.0 * rc + 1.0, d) * occ);
+            }
         }
     }
-    if (best_t < 0) { best_t = gp.n_tables - 1; best_rc = 2; }
+    if (best_t < 0) { best_t = gp.n_tables - 1; best_rc = 2; gp.expect_cand = 1e9f; }
     int t = best_t, rc = best_rc;
     while (gp.n_attempts < GRID_MAX_ATTEMPTS) {
         gp.att_tab[gp.n_attempts] = (unsigned char)t;

@@ -126,6 +126,7 @@ int  opt_queue_cap();
 int  opt_grid();
 int  opt_grid_tma();
 int  opt_grid_pair();
+void note_grid_pair_used(int used);
 int  opt_sort_bits();
 size_t opt_pool_keep_bytes();
 int  opt_pool_guard();

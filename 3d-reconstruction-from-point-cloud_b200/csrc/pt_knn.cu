@@ -441,7 +441,7 @@ int launch_query(pt_index *ix, const QueryParams &qp_in, cudaStream_t s)
             fprintf(stderr, " (level %d, rc %d, occ %.1f)", L, (int)qp.grid.att_rc[a],
                     (double)ix->n / (double)ix->level_cells[L]);
         }
-        fprintf(stderr, "\n");
+        fprintf(stderr, "; ~%.0f candidates expected in the first\n", (double)qp.grid.expect_cand);
     }
     if (variant == 6 && !have_grid) variant = -1;
     if (variant < 0) {

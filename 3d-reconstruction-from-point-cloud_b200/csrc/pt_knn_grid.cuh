@@ -29,9 +29,6 @@
 
 namespace pt {
 
-#ifndef PT_PAIR_OPT
-#define PT_PAIR_OPT 6
-#endif
 constexpr int GRID_CAP = 256;         // staged candidates per sample (8-bit slot numbers)
 #ifndef PT_GRID_WARPS
 #define PT_GRID_WARPS 4
@@ -139,18 +136,11 @@ __device__ __forceinline__ void grid_lookup(const GridBucket *buckets, uint32_t 
             const uint32_t total = c.x & 0xffffu;
             if (total == 0xffffu) { cnt = 0xffffffffu; return; }
             const unsigned r1 = rank + 1;
-#if PT_PAIR_OPT & 8
             // 16-bit field r of the 128-bit cum[]: pick the 64-bit half, then two bytes of it
             const uint32_t bx = rank < 4 ? c.x : c.z, by = rank < 4 ? c.y : c.w;
             const uint32_t ex = r1 < 4 ? c.x : c.z, ey = r1 < 4 ? c.y : c.w;
             const uint32_t beg = rank ? (__byte_perm(bx, by, 0x4410u + 0x22u * (rank & 3u)) & 0xffffu) : 0u;
             const uint32_t end = rank < 7 ? (__byte_perm(ex, ey, 0x4410u + 0x22u * (r1 & 3u)) & 0xffffu) : total;
-#else
-            const unsigned long long lo = (unsigned long long)c.x | ((unsigned long long)c.y << 32);
-            const unsigned long long hi = (unsigned long long)c.z | ((unsigned long long)c.w << 32);
-            const uint32_t beg = rank ? (uint32_t)((rank < 4 ? lo >> (16 * rank) : hi >> (16 * (rank - 4))) & 0xffffu) : 0u;
-            const uint32_t end = rank < 7 ? (uint32_t)((r1 < 4 ? lo >> (16 * r1) : hi >> (16 * (r1 - 4))) & 0xffffu) : total;
-#endif
             start = a.x + beg;
             cnt = end - beg;
             return;
@@ -621,14 +611,10 @@ __device__ __forceinline__ void pair_select(const PointF *cand, uint32_t total, 
     uint32_t m = GKEY_NONE;
 #pragma unroll 2
     for (int r = 0; r <= k; ++r) {
-#if PT_PAIR_OPT & 2
         // two independent full-warp REDUX.MIN, each over one half's heads
         const uint32_t mA = __reduce_min_sync(0xffffffffu, upper ? GKEY_NONE : h[0]);
         const uint32_t mB = __reduce_min_sync(0xffffffffu, upper ? h[0] : GKEY_NONE);
         m = upper ? mB : mA;
-#else
-        m = seg16_min(h[0]);
-#endif
         if ((unsigned)r == sl) mine = m;
         if ((m & 15u) == sl) {             // the owner pops its head
 #pragma unroll
@@ -782,7 +768,6 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
     const PointF *pts = reinterpret_cast<const PointF *>(P.pts);
     uint32_t p = blockIdx.x * GRID_WARPS + wib;
     if (p >= n_pairs) return;
-#if PT_PAIR_OPT & 4
     while (p < n_pairs) {
         // a pair whose second sample does not exist answers the first one twice and emits it once
         const bool valid = 2u * p + (lane >> 4) < P.m;
@@ -791,23 +776,6 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
                      qz = __ldg(P.queries + 3 * (size_t)s + 2);
         if (lane == 0 && p + n_warps < n_pairs)      // the next pair's coordinates: towards L2 meanwhile
             asm volatile("prefetch.global.L2 [%0];" ::"l"(P.queries + 6 * (size_t)(p + n_warps)));
-#else
-    // a pair whose second sample does not exist answers the first one twice and emits it once
-    uint32_t s = min(2u * p + (lane >> 4), P.m - 1u);
-    double qx = __ldg(P.queries + 3 * (size_t)s), qy = __ldg(P.queries + 3 * (size_t)s + 1),
-           qz = __ldg(P.queries + 3 * (size_t)s + 2);
-    while (p < n_pairs) {
-        const bool valid = 2u * p + (lane >> 4) < P.m;
-        const uint32_t pn = p + n_warps;
-        uint32_t sn = s;
-        double nx = 0.0, ny = 0.0, nz = 0.0;
-        if (pn < n_pairs) {
-            sn = min(2u * pn + (lane >> 4), P.m - 1u);
-            nx = __ldg(P.queries + 3 * (size_t)sn);
-            ny = __ldg(P.queries + 3 * (size_t)sn + 1);
-            nz = __ldg(P.queries + 3 * (size_t)sn + 2);
-        }
-#endif
         const double r2 = P.r2_per_query ? __ldg(P.r2_per_query + s) : P.r2;
         // ---- the sample's cell and its distance to the faces of the 3^3 block (see grid_sample) ---
         const GridTable &T = G.tab[G.att_tab[0]];
@@ -907,15 +875,6 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
         pair_emit(P, s, done, mine, d, li, lane, wcand);
         // ---- halves this attempt could not finish: the whole warp, the whole schedule ----------------
         const uint32_t redo = __ballot_sync(0xffffffffu, valid && !done);
-#if PT_PAIR_OPT & 16
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-            if (((redo >> (16 * hh)) & 1u) == 0u) continue;
-            const double fx = __shfl_sync(0xffffffffu, qx, 16 * hh), fy = __shfl_sync(0xffffffffu, qy, 16 * hh),
-                         fz = __shfl_sync(0xffffffffu, qz, 16 * hh);
-            grid_sample<PointF, true>(P, 2u * p + (uint32_t)hh, fx, fy, fz, lane, wcand, bar, phase, ovf_count, ovf_list);
-        }
-#else
         if (redo & 1u) {
             const double fx = __shfl_sync(0xffffffffu, qx, 0), fy = __shfl_sync(0xffffffffu, qy, 0),
                          fz = __shfl_sync(0xffffffffu, qz, 0);
@@ -926,12 +885,7 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
                          fz = __shfl_sync(0xffffffffu, qz, 16);
             grid_sample<PointF, true>(P, 2u * p + 1u, fx, fy, fz, lane, wcand, bar, phase, ovf_count, ovf_list);
         }
-#endif
-#if PT_PAIR_OPT & 4
         p += n_warps;
-#else
-        p = pn; s = sn; qx = nx; qy = ny; qz = nz;
-#endif
     }
 }
 
@@ -961,10 +915,15 @@ static int launch_grid(const QueryParams &qp, int sm_count, uint32_t *count, uin
 {
     const size_t smem = grid_kernel_smem(sizeof(PT));
     const bool tma = opt_grid_tma() != 0;
-    // two samples per warp when the lists fit a half-warp and the first attempt is a 3^3 block
+    // two samples per warp when the lists fit a half-warp, the first attempt is a 3^3 block and
+    // its candidates are expected to fit the half-warp's staging area with ~35 % to spare (a
+    // sample with more is redone by the whole warp: correct, but the first pass was wasted)
     if (std::is_same<PT, PointF>::value && tma && opt_grid_pair() != 0 && qp.k <= 16 && qp.grid.n_attempts > 0 &&
-        qp.grid.att_rc[0] == 1)
+        qp.grid.att_rc[0] == 1 && (opt_grid_pair() == 2 || qp.grid.expect_cand <= 0.74f * (float)PAIR_CAP)) {
+        note_grid_pair_used(1);
         return launch_grid_pair(qp, sm_count, count, list, s);
+    }
+    note_grid_pair_used(0);
     auto kern = tma ? knn_grid_kernel<PT, true> : knn_grid_kernel<PT, false>;
     if (smem > 48 * 1024)
         PT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

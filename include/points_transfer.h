@@ -275,7 +275,9 @@ int pt_texture_render_lists(const void *points, size_t n, const void *vertices, 
  * the samples it hands over; 6 grid, 5 scan kernel, 2 thread kernel, 0 warp kernel),
  * "order" (0 Morton, 1 Hilbert [default], 2 Hilbert + kd refinement: no cell tables),
  * "grid" (1 build the uniform-grid cell tables [default]), "grid_tma" (1 stage candidate runs
- * with cp.async.bulk [default], 0 per-lane cp.async), "sort_bits" (ordered key bits from the top, 8 per
+ * with cp.async.bulk [default], 0 per-lane cp.async), "grid_pair" (1 [default]: two samples per
+ * warp when k <= 16 and the first attempt's candidates are expected to fit a half-warp; 2: whenever
+ * k <= 16; 0: never; the read-only "grid_pair_used" tells what the last launch did), "sort_bits" (ordered key bits from the top, 8 per
  * radix pass; default 0 = auto: 40 up to 2^27 points, else 48),
  * "pool_keep_mb" (build temporaries kept cached in the library's private memory pool after a
  * build or a free, default 2048: a rebuild of a larger index maps fresh memory again),

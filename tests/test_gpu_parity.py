@@ -39,6 +39,7 @@ def _default_options(pkg):
     pkg.set_option("grid_tma", 1)
     pkg.set_option("pool_guard", 0)
     pkg.set_option("sort_bits", 0)
+    pkg.set_option("grid_pair", 1)
 
 
 # (knn_variant, order): grid / thread / warp / scan kernel x Morton, Hilbert, Hilbert + kd
@@ -531,3 +532,34 @@ def test_any_number_of_ordered_key_bits_is_exact(bits, pkg, pto, torch_cuda):
             out = t.transfer(V, k, want_idx=True, want_d2=True)
         assert np.array_equal(out["idx"], ref_idx), (bits, variant)
         assert np.array_equal(out["d2"], ref_d2)
+
+
+@pytest.mark.parametrize("k,radius", [(1, None), (7, None), (16, None), (16, 0.35), (12, 0.05)])
+def test_two_samples_per_warp_equals_one_sample_per_warp(k, radius, pkg, pto, torch_cuda):
+    """The grid kernel answers two samples per warp when k <= 16 (option "grid_pair", default on)
+    and one per warp otherwise.  Both forms against the oracle on: an odd number of samples (the
+    last pair is half empty), a single sample, a scanned surface, a lattice (every selection is
+    ambiguous after truncation: the exact (d2, index) selection runs in both halves), and a cloud
+    with a cluster far denser than the rest (more candidates than a half-warp stages: those
+    samples are redone by the whole warp)."""
+    rng = np.random.default_rng(5)
+    surf = pkg.synth.cloud_host(120_001, seed=19, side=50.0)
+    g = np.arange(40, dtype=np.float64) * 0.25
+    lat = pkg.api.make_points(np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3))
+    dense = pkg.synth.cloud_host(60_000, seed=23, side=50.0)
+    blob = np.float32(25.0 + 0.4 * rng.standard_normal((40_000, 3))).astype(np.float64)
+    dense = np.concatenate([dense, pkg.api.make_points(blob)])
+    for name, P, V in (("surface", surf, pkg.synth.samples_host(41, side=50.0)),          # 1 681 samples: odd
+                       ("one", surf, pkg.synth.samples_host(41, side=50.0)[777:778]),
+                       ("lattice", lat, pkg.api.make_points(lat["ver"][::37] + 0.125)),
+                       ("blob", dense, pkg.api.make_points(np.float32(25.0 + 0.5 * rng.standard_normal((999, 3))).astype(np.float64)))):
+        ref_idx, ref_d2 = pto.KdTree(P).knn(V, k, radius=-1.0 if radius is None else radius, exact_ties=True)
+        ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+        for pair in (2, 1, 0):            # 2: two per warp whatever the expected candidate count
+            pkg.set_option("grid_pair", pair)
+            pkg.set_option("knn_variant", 6)
+            with pkg.Tree(P) as t:
+                out = t.transfer(V, k, radius=radius, want_idx=True, want_d2=True)
+            assert np.array_equal(out["idx"], ref_idx), (name, pair)
+            assert np.array_equal(out["d2"], ref_d2), (name, pair)
+            _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
