@@ -17,7 +17,7 @@ static std::atomic<int> g_sort{1};    // 1 hand-written radix sort (default), 0 
 static std::atomic<int> g_order{1};   // 0 Morton, 1 Hilbert (default), 2 Hilbert + kd refinement (no cell tables)
 static std::atomic<int> g_grid{1};        // build the uniform-grid cell tables (pt_grid.cu)
 static std::atomic<int> g_grid_tma{1};    // stage candidate runs with cp.async.bulk (0: per-lane cp.async)
-static std::atomic<int> g_pool_keep_mb{2048};   // temporaries kept cached in the library's pool after a build / free
+static std::atomic<int> g_pool_keep_mb{-1};   // memory kept cached in the library's pool after a build / free; < 0: a quarter of the device
 static std::atomic<int> g_sort_bits{0};   // ordered key bits, from the top; 0 = auto (40 or 48: cells contiguous down to level 13 / 16)
 
 bool verbose()
@@ -53,7 +53,14 @@ int opt_grid_pair() { return g_grid_pair.load(); }
 static std::atomic<int> g_grid_pair_used{0};   // introspection: did the last grid launch run two samples per warp
 void note_grid_pair_used(int used) { g_grid_pair_used.store(used); }
 int opt_sort_bits() { return g_sort_bits.load(); }
-size_t opt_pool_keep_bytes() { return (size_t)g_pool_keep_mb.load() << 20; }
+size_t opt_pool_keep_bytes()
+{
+    const int mb = g_pool_keep_mb.load();
+    if (mb >= 0) return (size_t)mb << 20;
+    size_t free_b = 0, total_b = 0;                       // auto: whatever the builds needed, up to 1/4 of the device
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (size_t)2048 << 20; }
+    return total_b / 4;
+}
 static std::atomic<int> g_pool_guard{0};   // debug: guard words around every device allocation (pt_build.cu)
 int opt_pool_guard() { return g_pool_guard.load(); }
 static std::atomic<int> g_host_chunks{8};   // host-buffer API: pipeline chunks per call (one stream each, up to 16)
@@ -77,7 +84,7 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "grid_tma")) { g_grid_tma.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "grid_pair")) { g_grid_pair.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { g_sort_bits.store(value); return PT_OK; }
-    if (!strcmp(name, "pool_keep_mb")) { g_pool_keep_mb.store(value < 0 ? 0 : value); return PT_OK; }
+    if (!strcmp(name, "pool_keep_mb")) { g_pool_keep_mb.store(value < 0 ? -1 : value); return PT_OK; }
     if (!strcmp(name, "pool_guard")) { g_pool_guard.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "smem_pad")) { g_smem_pad.store(value < 0 ? 0 : value); return PT_OK; }
     if (!strcmp(name, "queue_cap")) { g_queue_cap.store(value < 2 ? 2 : value); return PT_OK; }
@@ -158,9 +165,11 @@ static void destroy_index(pt_index *ix)
     pool_free(ix->pts, ix->stream);
     pool_free(ix->boxes, ix->stream);
     pool_free(ix->grid_mem, ix->stream);
+    pool_free(ix->attrs, ix->stream);         // (attributes and ids too: cudaMalloc / cudaFree of 0.8 GB cost milliseconds)
+    pool_free(ix->ids, ix->stream);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" (default 2 GiB) stays cached for the next build
-    dev_free(ix->attrs); dev_free(ix->ids); dev_free(ix->fallback_word); dev_free(ix->inv_perm);
+    pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" of it stays mapped for the next build
+    dev_free(ix->fallback_word); dev_free(ix->inv_perm);
     dev_free(ix->ws_raw); dev_free(ix->ws_q); dev_free(ix->ws_out);
     for (auto &c : ix->cs) if (c) cudaStreamDestroy(c);
     for (auto &e : ix->cev) if (e) cudaEventDestroy(e);
@@ -244,7 +253,7 @@ int pt_index_build(const void *points, size_t n, const pt_build_opts *opts, pt_i
     int rc = ingest_points_aos(ix, points, n, mode, &xyz, &representable);
     if (rc == PT_OK && mode == PT_COORD_F32 && !representable) rc = PT_ERR_NOT_REPRESENTABLE;
     if (rc == PT_OK && opts && opts->ids && n) {
-        cudaError_t e = dev_alloc((void **)&ix->ids, sizeof(int32_t) * n) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
+        cudaError_t e = pool_alloc((void **)&ix->ids, sizeof(int32_t) * n, ix->stream) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(ix->ids, opts->ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice,
                                 ix->stream);
@@ -269,14 +278,14 @@ int pt_index_build_device(const void *pos, int coord_f64, const pt_attr *attrs,
     PT_TRY(new_index(device, &ix));
     int rc = PT_OK;
     if (n && attrs) {
-        cudaError_t e = dev_alloc((void **)&ix->attrs, sizeof(pt_attr) * n) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
+        cudaError_t e = pool_alloc((void **)&ix->attrs, sizeof(pt_attr) * n, ix->stream) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(ix->attrs, attrs, sizeof(pt_attr) * n, cudaMemcpyDeviceToDevice,
                                 ix->stream);
         rc = map_cuda_error(e);
     }
     if (rc == PT_OK && n && ids) {
-        cudaError_t e = dev_alloc((void **)&ix->ids, sizeof(int32_t) * n) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
+        cudaError_t e = pool_alloc((void **)&ix->ids, sizeof(int32_t) * n, ix->stream) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation;
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(ix->ids, ids, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice,
                                 ix->stream);

@@ -716,7 +716,7 @@ static int build_impl(pt_index *ix, In in, uint32_t n)
     pool_free(arena, s);
     arena_guard.p = nullptr;
     cudaStreamSynchronize(s);
-    pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" (default 2 GiB) of temporaries stays cached
+    pool_trim(ix->device, opt_pool_keep_bytes());   // "pool_keep_mb" of it stays mapped for the next build
     ix->device_bytes = sizeof(Out) * n_pad + sizeof(Box) * total + ix->grid_bytes +
                        (ix->attrs ? sizeof(pt_attr) * (size_t)n : 0) +
                        (ix->ids ? sizeof(int32_t) * (size_t)n : 0);
@@ -814,7 +814,7 @@ int ingest_points_aos(pt_index *ix, const void *points, size_t n, int coord_mode
     // chunked upload through two device staging buffers
     const size_t chunk = (size_t)1 << 22;  // 4 Mi records = 320 MiB per buffer
     const size_t cap = n < chunk ? n : chunk;
-    if (got(dev_alloc((void **)&xyz, sizeof(double) * 3 * n)) && got(dev_alloc((void **)&ix->attrs, sizeof(pt_attr) * n)) &&
+    if (got(dev_alloc((void **)&xyz, sizeof(double) * 3 * n)) && got(pool_alloc((void **)&ix->attrs, sizeof(pt_attr) * n, s)) &&
         got(dev_alloc((void **)&flag, sizeof(unsigned int))) && ok(cudaMemsetAsync(flag, 0, sizeof(unsigned int), s)) &&
         got(dev_alloc((void **)&stage[0], sizeof(Raw80) * cap)) && got(dev_alloc((void **)&stage[1], sizeof(Raw80) * cap)) &&
         ok(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)) &&

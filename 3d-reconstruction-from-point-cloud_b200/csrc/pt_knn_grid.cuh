@@ -25,6 +25,11 @@
 //      candidates is handed to the box-pyramid kernels (exact for any geometry);
 //   5. winners' attributes gathered one per lane; the frozen blend's sequential fp64 sums run
 //      one component per lane over a transposed shared-memory tile (bit-identical to BlendAcc).
+//
+// Two kernels share these steps: knn_grid_kernel (one sample per warp, any k <= 32, float4 or
+// fp64 records, the whole attempt schedule) and knn_grid_pair_kernel (two samples per warp, 16
+// lanes each, for k <= 16 on float4 records when the first attempt is a 3^3 block expected to
+// stage fewer candidates than a half-warp holds; see the comment above it).  launch_grid picks.
 #pragma once
 
 namespace pt {

@@ -451,7 +451,8 @@ extern "C" int pt_texture_render_lists(const void *points, size_t n, const void 
     }
     if (tmp.stream) cudaStreamSynchronize(tmp.stream);
     dev_free(xyz);
-    dev_free(tmp.attrs);
+    pool_free(tmp.attrs, tmp.stream);
+    if (tmp.stream) cudaStreamSynchronize(tmp.stream);
     if (tmp.stream) cudaStreamDestroy(tmp.stream);
     cudaGetLastError();
     return rc;
