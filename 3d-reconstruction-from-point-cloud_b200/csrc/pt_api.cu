@@ -50,6 +50,12 @@ int opt_grid() { return g_grid.load(); }
 int opt_grid_tma() { return g_grid_tma.load(); }
 static std::atomic<int> g_grid_pair{1};   // grid kernel: two samples per warp when k <= 16
 int opt_grid_pair() { return g_grid_pair.load(); }
+static std::atomic<int> g_grid_min_occ10{40};    // finest table: finest level with >= this / 10 points per occupied cell
+static std::atomic<int> g_grid_lookup_cost{8};   // grid_plan: cost of one bucket look-up, in candidates
+static std::atomic<int> g_grid_admit100{100};    // grid_plan: a block is tried first when rc cells >= this / 100 expected k-th distances
+int opt_grid_admit100() { return g_grid_admit100.load(); }
+int opt_grid_min_occ10() { return g_grid_min_occ10.load(); }
+int opt_grid_lookup_cost() { return g_grid_lookup_cost.load(); }
 static std::atomic<int> g_grid_pair_used{0};   // introspection: did the last grid launch run two samples per warp
 void note_grid_pair_used(int used) { g_grid_pair_used.store(used); }
 int opt_sort_bits() { return g_sort_bits.load(); }
@@ -82,6 +88,9 @@ int set_option(const char *name, int value)
     if (!strcmp(name, "sort")) { g_sort.store(value); return PT_OK; }
     if (!strcmp(name, "grid")) { g_grid.store(value ? 1 : 0); return PT_OK; }
     if (!strcmp(name, "grid_tma")) { g_grid_tma.store(value ? 1 : 0); return PT_OK; }
+    if (!strcmp(name, "grid_min_occ10")) { g_grid_min_occ10.store(value < 5 ? 5 : value); return PT_OK; }
+    if (!strcmp(name, "grid_lookup_cost")) { g_grid_lookup_cost.store(value < 0 ? 0 : value); return PT_OK; }
+    if (!strcmp(name, "grid_admit100")) { g_grid_admit100.store(value < 10 ? 10 : value); return PT_OK; }
     if (!strcmp(name, "grid_pair")) { g_grid_pair.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { g_sort_bits.store(value); return PT_OK; }
     if (!strcmp(name, "pool_keep_mb")) { g_pool_keep_mb.store(value < 0 ? -1 : value); return PT_OK; }
@@ -100,6 +109,9 @@ int get_option(const char *name, int *value)
     if (!strcmp(name, "sort")) { *value = g_sort.load(); return PT_OK; }
     if (!strcmp(name, "grid")) { *value = g_grid.load(); return PT_OK; }
     if (!strcmp(name, "grid_tma")) { *value = g_grid_tma.load(); return PT_OK; }
+    if (!strcmp(name, "grid_min_occ10")) { *value = g_grid_min_occ10.load(); return PT_OK; }
+    if (!strcmp(name, "grid_lookup_cost")) { *value = g_grid_lookup_cost.load(); return PT_OK; }
+    if (!strcmp(name, "grid_admit100")) { *value = g_grid_admit100.load(); return PT_OK; }
     if (!strcmp(name, "grid_pair")) { *value = g_grid_pair.load(); return PT_OK; }
     if (!strcmp(name, "grid_pair_used")) { *value = g_grid_pair_used.load(); return PT_OK; }
     if (!strcmp(name, "sort_bits")) { *value = g_sort_bits.load(); return PT_OK; }

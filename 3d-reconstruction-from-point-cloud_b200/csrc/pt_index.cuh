@@ -126,6 +126,9 @@ int  opt_queue_cap();
 int  opt_grid();
 int  opt_grid_tma();
 int  opt_grid_pair();
+int  opt_grid_min_occ10();
+int  opt_grid_admit100();
+int  opt_grid_lookup_cost();
 void note_grid_pair_used(int used);
 int  opt_sort_bits();
 size_t opt_pool_keep_bytes();

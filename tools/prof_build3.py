@@ -9,6 +9,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 keeps = [int(x) for x in sys.argv[3:]] or [-1]
 w = pkg.synth.CONFIGS["cfg2"]
 pos, attrs = pkg.synth.cloud_device(n, w.seed)
+if os.environ.get("PT_SORT"):
+    pkg.set_option("sort", int(os.environ["PT_SORT"]))      # 0: cub::DeviceRadixSort (comparison only)
 for keep in keeps:
     pkg.set_option("pool_keep_mb", keep)
     ms, wall = [], []

@@ -14,9 +14,14 @@ g = int(a[2] or 0) or w.gu
 k = int(a[3] or 0) or w.k
 reps = int(a[4] or 3)
 torch.cuda.set_device(0)
+for o in ("grid_min_occ10", "grid_lookup_cost", "grid_admit100"):
+    if os.environ.get("PT_" + o.upper()):
+        pkg.set_option(o, int(os.environ["PT_" + o.upper()]))
 pkg.set_option("verbose", 1)
-pos, attrs = pkg.synth.cloud_device(n, w.seed, kind=w.kind, sigma=w.sigma)
-q = pkg.synth.samples_device(g, g, center=w.center)
+slab = int(os.environ.get("PT_SLAB", "1"))       # PT_SLAB=8: one of 8 x-slabs of the workload (n = its points)
+u1 = pkg.synth.L_DOMAIN / slab
+pos, attrs = pkg.synth.cloud_device(n, w.seed, u0=0.0, u1=u1, kind=w.kind, sigma=w.sigma)
+q = pkg.synth.samples_device(g // slab, g, u0=0.0, u1=u1, center=w.center)
 m = q.shape[0]
 tree = pkg.DeviceTree(pos, attrs)
 pkg.set_option("verbose", 0)
