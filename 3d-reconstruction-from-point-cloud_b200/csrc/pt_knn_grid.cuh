@@ -782,6 +782,10 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
         if (lane == 0 && p + n_warps < n_pairs)      // the next pair's coordinates: towards L2 meanwhile
             asm volatile("prefetch.global.L2 [%0];" ::"l"(P.queries + 6 * (size_t)(p + n_warps)));
         const double r2 = P.r2_per_query ? __ldg(P.r2_per_query + s) : P.r2;
+        // a negative / NaN bound admits nothing: the empty answer is final (the unused rows of the
+        // sharded path's fixed-capacity blocks arrive like this)
+        const bool dead = valid && !(r2 >= 0.0);
+        const bool look = valid && !dead;
         // ---- the sample's cell and its distance to the faces of the 3^3 block (see grid_sample) ---
         const GridTable &T = G.tab[G.att_tab[0]];
         const int sh = 21 - T.level;
@@ -812,8 +816,8 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
             const uint32_t n1 = sl + 16u;
             const uint32_t x0 = c[0] + sl % 3u - 1u, y0 = c[1] + (sl / 3u) % 3u - 1u, z0 = c[2] + sl / 9u - 1u;
             const uint32_t x1 = c[0] + n1 % 3u - 1u, y1 = c[1] + (n1 / 3u) % 3u - 1u, z1 = c[2] + n1 / 9u - 1u;
-            const bool ok0 = valid && x0 < ncell && y0 < ncell && z0 < ncell;
-            const bool ok1 = valid && n1 < 27u && x1 < ncell && y1 < ncell && z1 < ncell;
+            const bool ok0 = look && x0 < ncell && y0 < ncell && z0 < ncell;
+            const bool ok1 = look && n1 < 27u && x1 < ncell && y1 < ncell && z1 < ncell;
             // (issuing both first probes before examining either was measured: the extra live
             // registers cost more than the second round trip)
             if (ok0) grid_lookup(T.buckets, T.cap, x0, y0, z0, st0, ct0);
@@ -830,7 +834,7 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, (int)(hbase | 15u));
         const bool dense_h = ((__ballot_sync(0xffffffffu, dense) >> hbase) & 0xffffu) != 0u;
-        const bool go = valid && !dense_h && total <= (uint32_t)PAIR_CAP && (total >= (uint32_t)k || r2 <= g2);
+        const bool go = look && !dense_h && total <= (uint32_t)PAIR_CAP && (total >= (uint32_t)k || r2 <= g2);
         const uint32_t tot = go ? total : 0u;
         const uint32_t tA = __shfl_sync(0xffffffffu, tot, 0), tB = __shfl_sync(0xffffffffu, tot, 16);
 #ifdef PT_STATS
@@ -876,7 +880,7 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
             d = dist2_exact(qx, qy, qz, px, py, pz);
         }
         const double kth = __shfl_sync(0xffffffffu, d, (int)hbase + k - 1);   // +inf while the list is short
-        const bool done = go && fmin(kth, r2) <= g2;
+        const bool done = dead || (go && fmin(kth, r2) <= g2);
         pair_emit(P, s, done, mine, d, li, lane, wcand);
         // ---- halves this attempt could not finish: the whole warp, the whole schedule ----------------
         const uint32_t redo = __ballot_sync(0xffffffffu, valid && !done);
