@@ -40,6 +40,9 @@ def _default_options(pkg):
     pkg.set_option("pool_guard", 0)
     pkg.set_option("sort_bits", 0)
     pkg.set_option("grid_pair", 1)
+    pkg.set_option("grid_admit100", 100)
+    pkg.set_option("grid_lookup_cost", 8)
+    pkg.set_option("grid_min_occ10", 40)
 
 
 # (knn_variant, order): grid / thread / warp / scan kernel x Morton, Hilbert, Hilbert + kd
@@ -562,4 +565,30 @@ def test_two_samples_per_warp_equals_one_sample_per_warp(k, radius, pkg, pto, to
                 out = t.transfer(V, k, radius=radius, want_idx=True, want_d2=True)
             assert np.array_equal(out["idx"], ref_idx), (name, pair)
             assert np.array_equal(out["d2"], ref_d2), (name, pair)
+            _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
+
+
+@pytest.mark.parametrize("min_occ10,admit100,lookup_cost", [(5, 10, 0), (5, 100, 8), (40, 30, 50), (400, 100, 8),
+                                                            (40, 300, 0), (2000, 10, 0)])
+def test_any_search_schedule_is_exact(min_occ10, admit100, lookup_cost, pkg, pto, torch_cuda):
+    """The constants behind the cell tables and the attempt schedule (finest level by points per
+    cell, how far a block must reach to be tried first, what a look-up costs) only decide how
+    much work an answer takes: tables down to 0.5 points per cell, schedules that start with
+    blocks far too small (every sample needs a second attempt or the hand-over) or far too large
+    -- all answer exactly, with one and with two samples per warp."""
+    pkg.set_option("grid_min_occ10", min_occ10)
+    pkg.set_option("grid_admit100", admit100)
+    pkg.set_option("grid_lookup_cost", lookup_cost)
+    P = pkg.synth.cloud_host(200_000, seed=61, side=80.0)
+    V = pkg.synth.samples_host(45, side=80.0)
+    kd = pto.KdTree(P)
+    for k, radius in ((16, None), (32, None), (5, 0.6)):
+        ref_idx, ref_d2 = kd.knn(V, k, radius=-1.0 if radius is None else radius)
+        ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+        for pair in (2, 0):
+            pkg.set_option("grid_pair", pair)
+            with pkg.Tree(P) as t:
+                out = t.transfer(V, k, radius=radius, want_idx=True, want_d2=True)
+            assert np.array_equal(out["idx"], ref_idx), (k, radius, pair)
+            assert np.array_equal(out["d2"], ref_d2)
             _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
