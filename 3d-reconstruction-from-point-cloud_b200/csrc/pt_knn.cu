@@ -672,19 +672,51 @@ ghost_check_kernel(const double *q, const double *d2, uint32_t m, int k, double 
 // all_to_all that follows needs no host synchronisation: row = (x, y, z, +inf) -- the 4th word
 // is the per-query squared bound of pt_query_device -- and rows past a block's count keep the
 // NaN bound the caller memsets (0xff), which every query kernel answers with an empty list.
+// Row numbers come from three levels of counting, so that half a million samples do not queue
+// up on n_ranks global counters (one atomic per sample: 200 us at 2 ranks): lanes with the same
+// destination are ranked by __match_any_sync, warps add to the block's shared counters, and one
+// thread per destination reserves the block's range with a single global atomic.
+constexpr int ROUTE_SMEM_RANKS = 64;
 __global__ void __launch_bounds__(256)
 route_samples_kernel(const double *q, uint32_t m, const double *cuts, int n_ranks, uint32_t cap,
                      double *send, int32_t *sel, uint32_t *counts, uint32_t *overflow_flag)
 {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m) return;
-    const double x = q[3 * (size_t)s];
-    int lo = 0, hi = n_ranks - 1;            // last r with cuts[r] <= x (cuts[0] = -inf)
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (cuts[mid] <= x) lo = mid; else hi = mid - 1;
+    __shared__ uint32_t s_cnt[ROUTE_SMEM_RANKS], s_base[ROUTE_SMEM_RANKS];
+    const bool block_level = n_ranks <= ROUTE_SMEM_RANKS;
+    const unsigned lane = threadIdx.x & 31;
+    if (block_level) {
+        if (threadIdx.x < ROUTE_SMEM_RANKS) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
     }
-    const uint32_t pos = atomicAdd(&counts[lo], 1u);
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s < m;
+    double x = 0.0;
+    int lo = 0;
+    if (valid) {
+        x = q[3 * (size_t)s];
+        int hi = n_ranks - 1;                    // last r with cuts[r] <= x (cuts[0] = -inf)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (cuts[mid] <= x) lo = mid; else hi = mid - 1;
+        }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? lo : -1);
+    const int leader = __ffs(peers) - 1;
+    const uint32_t in_warp = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    uint32_t wbase = 0;
+    if (valid && (int)lane == leader)
+        wbase = block_level ? atomicAdd(&s_cnt[lo], (uint32_t)__popc(peers))
+                            : atomicAdd(&counts[lo], (uint32_t)__popc(peers));
+    wbase = __shfl_sync(0xffffffffu, wbase, leader);
+    uint32_t pos = wbase + in_warp;
+    if (block_level) {
+        __syncthreads();
+        if ((int)threadIdx.x < n_ranks)
+            s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
+        __syncthreads();
+        pos += s_base[lo];
+    }
+    if (!valid) return;
     if (pos >= cap) { atomicOr(overflow_flag, 1u); return; }
     double *row = send + ((size_t)lo * cap + pos) * 4;
     row[0] = x; row[1] = q[3 * (size_t)s + 1]; row[2] = q[3 * (size_t)s + 2]; row[3] = INFINITY;

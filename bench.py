@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--halo", type=float, default=-1.0, help="N > 1: ghost-zone width (0 = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=0,
+                    help="diagnosis: after the timed region run this many steps under torch.profiler and "
+                         "print rank 0's kernel table to stderr (never part of a reported number)")
     return ap.parse_args()
 
 
@@ -542,6 +545,16 @@ def main():
     ms_per_step, ms_per_rank, host_issue_ms, launches = timed_steps(pkg, torch, dist, world, dev, step, flush,
                                                                     args.steps, args.warmup)
     clocks = sampler.stop()
+    if args.profile_steps > 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(args.profile_steps):
+                flush.zero_()
+                step()
+            torch.cuda.synchronize()
+        if rank == 0:
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70),
+                  file=sys.stderr)
     if st is not None and not st.validate():
         raise SystemExit("a routing / halo block overflowed or a sample left the ghost zone during the "
                          "timed steps: results invalid")
