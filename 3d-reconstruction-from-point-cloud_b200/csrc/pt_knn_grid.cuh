@@ -856,7 +856,8 @@ knn_grid_pair_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_lis
         uint32_t mine = GKEY_NONE;
         bool amb = false;
         const uint32_t tmax = max(tA, tB);
-        if (tmax <= 32u) pair_select<2>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
+        if (tmax == 0u) { /* nothing staged (unused rows, empty blocks): no key to select */ }
+        else if (tmax <= 32u) pair_select<2>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
         else if (tmax <= 64u) pair_select<4>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
 #if PT_PAIR_CAP > 128
         else if (tmax <= 128u) pair_select<8>(cand, tot, qx, qy, qz, r2, k, sl, hbase != 0u, mine, amb);
