@@ -576,6 +576,9 @@ knn_grid_kernel(const QueryParams P, uint32_t *ovf_count, uint32_t *ovf_list)
 // by this first attempt (list not full, more than PAIR_CAP candidates, dense bucket, k-th
 // distance beyond the block) is redone by the whole warp through grid_sample -- the complete
 // attempt schedule, staging rounds and the hand-over to the box-pyramid kernels.
+// (Two neighbours per sub-lane for 16 < k <= 32 was built and measured: exact, but 1.74 ms against
+// the one-sample kernel's 1.55 ms at k = 32 on a 125 M-point slab of cfg4 and 1.19 against 1.21 ms
+// at k = 20 -- with ~140 candidates per sample the work is data-parallel already; removed.)
 #ifndef PT_PAIR_CAP
 #define PT_PAIR_CAP 192
 #endif
@@ -727,10 +730,12 @@ __device__ __forceinline__ void pair_emit(const QueryParams &P, uint32_t s, bool
         for (; j < cnt; ++j) acc = __dadd_rn(acc, row[j]);
     }
     double s0 = __shfl_sync(0xffffffffu, acc, (int)hbase);
+    // (the nearest neighbour's attributes are fetched by every lane: only one half may need them,
+    // and a *_sync shuffle must not sit in a branch that half a warp takes)
+    const uint32_t c0 = __shfl_sync(0xffffffffu, at.rgba, (int)hbase);
+    const float n0x = __shfl_sync(0xffffffffu, at.nx, (int)hbase), n0y = __shfl_sync(0xffffffffu, at.ny, (int)hbase),
+                n0z = __shfl_sync(0xffffffffu, at.nz, (int)hbase);
     if (bl && !(s0 > 0.0 && s0 < INFINITY)) {   // overflowed weights: nearest neighbour only
-        const uint32_t c0 = __shfl_sync(0xffffffffu, at.rgba, (int)hbase);   // (all lanes of the half are here)
-        const float n0x = __shfl_sync(0xffffffffu, at.nx, (int)hbase), n0y = __shfl_sync(0xffffffffu, at.ny, (int)hbase),
-                    n0z = __shfl_sync(0xffffffffu, at.nz, (int)hbase);
         const double v[7] = {1.0, (double)(c0 & 0xffu), (double)((c0 >> 8) & 0xffu), (double)((c0 >> 16) & 0xffu),
                              (double)n0x, (double)n0y, (double)n0z};
         acc = 0.0;

@@ -537,10 +537,12 @@ def test_any_number_of_ordered_key_bits_is_exact(bits, pkg, pto, torch_cuda):
         assert np.array_equal(out["d2"], ref_d2)
 
 
-@pytest.mark.parametrize("k,radius", [(1, None), (7, None), (16, None), (16, 0.35), (12, 0.05)])
+@pytest.mark.parametrize("k,radius", [(1, None), (7, None), (16, None), (16, 0.35), (12, 0.05), (17, None),
+                                      (20, None), (32, None), (32, 0.5), (31, 0.08)])
 def test_two_samples_per_warp_equals_one_sample_per_warp(k, radius, pkg, pto, torch_cuda):
-    """The grid kernel answers two samples per warp when k <= 16 (option "grid_pair", default on)
-    and one per warp otherwise.  Both forms against the oracle on: an odd number of samples (the
+    """The grid kernel answers two samples per warp (16 lanes each; two neighbours per lane when
+    k > 16) when the first attempt is expected to fit (option "grid_pair", default on) and one per
+    warp otherwise.  Both forms against the oracle on: an odd number of samples (the
     last pair is half empty), a single sample, a scanned surface, a lattice (every selection is
     ambiguous after truncation: the exact (d2, index) selection runs in both halves), and a cloud
     with a cluster far denser than the rest (more candidates than a half-warp stages: those
@@ -592,3 +594,34 @@ def test_any_search_schedule_is_exact(min_occ10, admit100, lookup_cost, pkg, pto
             assert np.array_equal(out["idx"], ref_idx), (k, radius, pair)
             assert np.array_equal(out["d2"], ref_d2)
             _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
+
+
+@pytest.mark.parametrize("k", [4, 16, 24])
+def test_overflowing_weights_in_one_half_of_a_pair(k, pkg, pto, torch_cuda):
+    """Frozen blend, overflow rule: a sample 1e-160 away from a point has d2 = 1e-320 and a weight
+    of +inf, so its blend falls back to the nearest neighbour alone.  Here that sample shares a
+    warp with an ordinary one (and with another of its kind): each half takes its own branch."""
+    rng = np.random.default_rng(11)
+    xyz = np.float32(rng.uniform(-1.0, 1.0, (20_000, 3))).astype(np.float64)
+    xyz[0] = 0.0
+    P = pkg.api.make_points(xyz, normal=rng.standard_normal((len(xyz), 3)),
+                            color=rng.integers(0, 256, (len(xyz), 3)))
+    q = np.float32(rng.uniform(-0.9, 0.9, (64, 3))).astype(np.float64)
+    q[0] = (1e-160, 0.0, 0.0)           # half A overflows, half B ordinary
+    q[3] = (0.0, -1e-160, 0.0)          # half B overflows
+    q[6] = (1e-160, 1e-160, 0.0)        # both halves
+    q[7] = (0.0, 0.0, 1e-161)
+    q[10] = (0.0, 0.0, 0.0)             # exact hit next to an overflowing one
+    q[11] = (1e-162, 0.0, 0.0)
+    V = pkg.api.make_points(q)
+    ref_idx, ref_d2 = pto.KdTree(P).knn(V, k)
+    ref_rgba, ref_nrm = pto.blend(P, ref_idx, ref_d2)
+    assert ref_d2[0, 0] > 0.0 and 1.0 / ref_d2[0, 0] == np.inf
+    for pair in (2, 0):
+        pkg.set_option("grid_pair", pair)
+        pkg.set_option("knn_variant", 6)
+        with pkg.Tree(P) as t:
+            out = t.transfer(V, k, want_idx=True, want_d2=True)
+        assert np.array_equal(out["idx"], ref_idx), pair
+        assert np.array_equal(out["d2"], ref_d2), pair
+        _check_blend(out["rgba"], out["normal"], ref_rgba, ref_nrm)
