@@ -591,7 +591,7 @@ def main():
         res["d2"] = d2
         torch.cuda.synchronize()
         verified = verify_by_ball(pkg, pto, torch, dist, world, rank, dev, own_pos, own_attrs, first, q, res,
-                                  k, w.radius, 48 if world == 1 else 24,
+                                  k, w.radius, 200 if world == 1 else 96,
                                   cuts=None if st is None else cuts)
 
     # ---- e2e with pinned host buffers ------------------------------------------------------------
