@@ -25,6 +25,8 @@ q = pkg.synth.samples_device(g // slab, g, u0=0.0, u1=u1, center=w.center)
 m = q.shape[0]
 tree = pkg.DeviceTree(pos, attrs)
 pkg.set_option("verbose", 0)
+if os.environ.get("PT_TMA"):
+    pkg.set_option("grid_tma", int(os.environ["PT_TMA"]))
 if os.environ.get("PT_PAIR"):
     pkg.set_option("grid_pair", int(os.environ["PT_PAIR"]))
 if os.environ.get("PT_VARIANT"):
