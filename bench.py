@@ -676,7 +676,9 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
+                     "frac_of_nominal_8tbs": achieved / 8000.0,
                      "traffic": tr["dram_bytes"] if tr else None,
+                     "traffic_gbs": tr["dram_bytes"] / (ms_per_step * 1e-3) / 1e9 if tr else None,
                      "traffic_source": tr["capture"] if tr else None,
                      "over_read_factor": tr.get("over_read_factor") if tr else None,
                      "l2_hit_pct": tr.get("l2_hit_pct") if tr else None,
