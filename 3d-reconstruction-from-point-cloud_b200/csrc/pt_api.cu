@@ -63,9 +63,18 @@ size_t opt_pool_keep_bytes()
 {
     const int mb = g_pool_keep_mb.load();
     if (mb >= 0) return (size_t)mb << 20;
-    size_t free_b = 0, total_b = 0;                       // auto: whatever the builds needed, up to 1/4 of the device
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (size_t)2048 << 20; }
-    return total_b / 4;
+    // auto: whatever the builds needed, up to 1/4 of the (current) device; asked once per device
+    static std::atomic<unsigned long long> quarter[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return (size_t)2048 << 20; }
+    unsigned long long q = quarter[dev].load();
+    if (q == 0) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (size_t)2048 << 20; }
+        q = total_b / 4;
+        quarter[dev].store(q);
+    }
+    return (size_t)q;
 }
 static std::atomic<int> g_pool_guard{0};   // debug: guard words around every device allocation (pt_build.cu)
 int opt_pool_guard() { return g_pool_guard.load(); }
