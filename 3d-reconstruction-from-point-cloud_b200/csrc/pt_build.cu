@@ -497,7 +497,7 @@ static int guard_arm(void *base, size_t bytes, cudaStream_t s, void **user)
     PT_CUDA(cudaMemsetAsync((char *)base + GUARD + bytes, 0xA5, GUARD, s));
     *user = (char *)base + GUARD;
     std::lock_guard<std::mutex> lock(g_guard_mutex);
-    g_guarded[*user] = bytes;
+    try { g_guarded[*user] = bytes; } catch (...) { return PT_ERR_OUT_OF_MEMORY; }
     return PT_OK;
 }
 

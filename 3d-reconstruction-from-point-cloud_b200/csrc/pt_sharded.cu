@@ -98,8 +98,8 @@ int build_slabs(pt_sharded *S)
     std::vector<int> status(R, PT_OK);
     std::vector<std::thread> th;
     const double h2 = S->halo * S->halo * (1.0 + 1e-9);
-    for (int r = 0; r < R; ++r) {
-        th.emplace_back([&, r] {
+    auto work = [&](int r) {
+          try {
             Slab &s = S->slabs[r];
             std::vector<Rec80> rec;
             std::vector<int32_t> ids;
@@ -123,7 +123,10 @@ int build_slabs(pt_sharded *S)
             o.coord_mode = S->coord_mode;
             o.ids = ids.data();
             status[r] = pt_index_build(rec.data(), rec.size(), &o, &s.index);
-        });
+          } catch (...) { status[r] = PT_ERR_OUT_OF_MEMORY; }     // nothing is thrown across the ABI
+    };
+    for (int r = 0; r < R; ++r) {
+        try { th.emplace_back(work, r); } catch (...) { work(r); }      // no thread to be had: inline
     }
     for (auto &t : th) t.join();
     for (int r = 0; r < R; ++r)
@@ -149,8 +152,8 @@ int sharded_query(pt_sharded *S, const void *queries, size_t m, int k, double ra
     for (int attempt = 0; attempt < 8; ++attempt) {
         std::vector<int> status(R, PT_OK), needs(R, 0);
         std::vector<std::thread> th;
-        for (int r = 0; r < R; ++r) {
-            th.emplace_back([&, r] {
+        auto work = [&](int r) {
+              try {
                 const std::vector<uint32_t> &sel = mine[r];
                 const size_t mr = sel.size();
                 if (mr == 0) return;
@@ -183,7 +186,10 @@ int sharded_query(pt_sharded *S, const void *queries, size_t m, int k, double ra
                     if (rgba_out) memcpy(rgba_out + d * 4, rgba.data() + j * 4, 4);
                     if (normal_out) memcpy(normal_out + d * 3, nrm.data() + j * 3, sizeof(float) * 3);
                 }
-            });
+              } catch (...) { status[r] = PT_ERR_OUT_OF_MEMORY; }
+        };
+        for (int r = 0; r < R; ++r) {
+            try { th.emplace_back(work, r); } catch (...) { work(r); }
         }
         for (auto &t : th) t.join();
         bool again = false;
@@ -214,6 +220,7 @@ int pt_sharded_build(const void *points, size_t n, const pt_sharded_opts *opts, 
     if (avail == 0) return PT_ERR_NO_DEVICE;
     pt_sharded *S = new (std::nothrow) pt_sharded();
     if (!S) return PT_ERR_OUT_OF_MEMORY;
+    try {
     const int R = opts->n_devices;
     S->slabs.resize(R);
     for (int r = 0; r < R; ++r) {
@@ -261,6 +268,11 @@ int pt_sharded_build(const void *points, size_t n, const pt_sharded_opts *opts, 
     if (rc != PT_OK) { delete S; return rc; }
     *out = S;
     return PT_OK;
+    } catch (...) {                 // host allocation failure: nothing is thrown across the ABI
+        free_slabs(S);
+        delete S;
+        return PT_ERR_OUT_OF_MEMORY;
+    }
 }
 
 int pt_sharded_free(pt_sharded *S)
@@ -275,14 +287,18 @@ int pt_sharded_knn(pt_sharded *S, const void *queries, size_t m, int k, double r
                    double *d2_out)
 {
     if (!idx_out && m) return PT_ERR_INVALID_ARG;
-    return sharded_query(S, queries, m, k, radius, idx_out, d2_out, nullptr, nullptr);
+    try {
+        return sharded_query(S, queries, m, k, radius, idx_out, d2_out, nullptr, nullptr);
+    } catch (...) { return PT_ERR_OUT_OF_MEMORY; }
 }
 
 int pt_sharded_transfer(pt_sharded *S, const void *queries, size_t m, int k, double radius, int32_t *idx_out,
                         double *d2_out, uint8_t *rgba_out, float *normal_out)
 {
     if ((!rgba_out && !normal_out) && m) return PT_ERR_INVALID_ARG;
-    return sharded_query(S, queries, m, k, radius, idx_out, d2_out, rgba_out, normal_out);
+    try {
+        return sharded_query(S, queries, m, k, radius, idx_out, d2_out, rgba_out, normal_out);
+    } catch (...) { return PT_ERR_OUT_OF_MEMORY; }
 }
 
 int pt_sharded_get_info(const pt_sharded *S, pt_sharded_info *info)
