@@ -233,7 +233,7 @@ void memory_report()
 
 }  // namespace
 
-int main(int argc, char **argv)
+static int run(int argc, char **argv)
 {
     std::string usage_str = "Usage: ./pointTransfer <input-point-cloud> <input-mesh>";
     std::vector<std::string> pos_args;
@@ -404,5 +404,19 @@ int main(int argc, char **argv)
     memory_report();
     pt_index_free(index);
     pt_sharded_free(sharded);
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    // like every error path of the reference: a message, exit code 0 (a header announcing more
+    // records than memory holds ends here instead of in std::terminate)
+    try {
+        return run(argc, argv);
+    } catch (const std::exception &e) {
+        std::cerr << "pointsTransfer: " << e.what() << std::endl;
+    } catch (...) {
+        std::cerr << "pointsTransfer: unexpected error" << std::endl;
+    }
     return 0;
 }

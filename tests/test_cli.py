@@ -56,6 +56,14 @@ def test_no_gpu_fails_loudly(cli, pkg, tmp_path):
     assert "no CUDA device" in r.stderr and not (tmp_path / "texture.png").exists()
 
 
+def test_header_announcing_more_than_memory_is_a_message_not_a_crash(cli, tmp_path):
+    with open(tmp_path / "huge.ply", "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 99999999999999\nend_header\n1 2 3 0 0 1 1 2 3\n")
+    r = subprocess.run([cli, str(tmp_path / "huge.ply"), str(tmp_path / "huge.ply")],
+                       capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and "pointsTransfer:" in r.stderr
+
+
 def test_bad_k_is_a_message_not_a_crash(cli, tmp_path):
     # every error path of the reference prints and returns 0 (:116-120, :137-141)
     for k in ("-3", "0", "99"):
