@@ -14,6 +14,12 @@ g = int(a[2] or 0) or w.gu
 k = int(a[3] or 0) or w.k
 reps = int(a[4] or 3)
 torch.cuda.set_device(0)
+if os.environ.get("PT_L2_GRAN"):      # experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes)
+    import ctypes
+    torch.zeros(1, device="cuda")
+    rt = ctypes.CDLL("libcudart.so.12")
+    v = ctypes.c_size_t(0)
+    print("set", rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["PT_L2_GRAN"]))), "get", rt.cudaDeviceGetLimit(ctypes.byref(v), 5), v.value)
 for o in ("grid_min_occ10", "grid_lookup_cost", "grid_admit100"):
     if os.environ.get("PT_" + o.upper()):
         pkg.set_option(o, int(os.environ["PT_" + o.upper()]))
