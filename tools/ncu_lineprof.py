@@ -17,6 +17,17 @@ tot=sum(int(d['# Samples']) for d in agg); ti=sum(int(d['Instructions Executed']
 print("instr/sample",ti/nq,"samples",tot)
 tots={s:sum(int(d[s] or 0) for d in agg) for s in stalls}
 print({k[6:]:round(100*v/tot,1) for k,v in sorted(tots.items(), key=lambda x:-x[1])[:9]})
+import os
+_root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "3d-reconstruction-from-point-cloud_b200", "csrc")
+_text = {}
+def _line(fn, no):                      # the line of the repo's own source (the capture carries none in CSV)
+    if fn not in _text:
+        try: _text[fn] = open(os.path.join(_root, fn)).read().split("\n")
+        except OSError: _text[fn] = []
+    t = _text[fn]
+    return t[no - 1].strip() if 0 < no <= len(t) else ""
+for d in agg:
+    if d['Source'].strip() in ("", "-"): d['Source'] = _line(d['file'], int(d['Line No']))
 for d in sorted(agg,key=lambda d:(d['file'],int(d['Line No']))):
     ie=int(d['Instructions Executed'])/nq; sm=int(d['# Samples'])
     if ie>=thr or sm>=0.008*tot:
