@@ -57,3 +57,16 @@ def test_both_arms_emit_the_same_config():
     assert bench.pick_workload(type("A", (), {"workload": "auto"})(), 2) == "cfg3"
     assert bench.pick_workload(type("A", (), {"workload": "auto"})(), 4) == "cfg3"
     assert bench.pick_workload(type("A", (), {"workload": "auto"})(), 8) == "cfg4"
+
+
+def test_traffic_record_belongs_to_the_shipped_kernel_source():
+    """roofline.traffic in the bench line comes from one committed `ncu --set full` capture and is
+    reported only while the kernel source it was captured on is unchanged (sha256): editing
+    pt_knn_grid.cuh without a fresh capture must be noticed here, not as a silent `null`."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rec = bench.ncu_traffic("cfg2", 16, "knn_grid_pair_kernel")
+    assert rec is not None and rec["dram_bytes"] > 0
+
